@@ -1,0 +1,191 @@
+/* CPU oracle (plain C) for the brute-force Tanimoto scan + top-k path.
+ * TEST INFRASTRUCTURE ONLY: loaded by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline ("port") leg through oracle/oracle_c.py.  The product never links this.
+ *
+ * Pinned by tests/test_oracle.py against the reference's own known answers and against the
+ * reference sources compiled verbatim (oracle/_ref), see oracle/oracle.py.
+ *
+ * Follows:
+ *   scoring            reference calculation_functors.cpp:6-20  (TanimotoFunctorCPU)
+ *   cutoff / zeroing   reference fingerprintdb_cuda.cu:100-102  (TanimotoFunctor)
+ *   survivors, order   reference fingerprintdb_cuda.cu:263-290, 366-380
+ *   fold               reference calculation_functors.cpp:22-41
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct {
+    float score;
+    uint32_t row;
+} cand_t;
+
+/* calculation_functors.cpp:6-20, one row. */
+static inline float score_row(const int32_t* q, const int32_t* d, int words)
+{
+    int total = 0, common = 0;
+    for (int i = 0; i < words; i++) {
+        const int32_t fp1 = q[i], fp2 = d[i];
+        total += __builtin_popcount((unsigned) fp1) + __builtin_popcount((unsigned) fp2);
+        common += __builtin_popcount((unsigned) (fp1 & fp2));
+    }
+    return (float) common / (float) (total - common);
+}
+
+/* canonical order: score descending, then row ascending. */
+static inline int better(cand_t a, cand_t b)
+{
+    return a.score > b.score || (a.score == b.score && a.row < b.row);
+}
+
+/* bounded "keep the k best" container: binary heap whose root is the WORST kept entry */
+typedef struct {
+    cand_t* h;
+    uint32_t n, cap;
+} heap_t;
+
+static void heap_push(heap_t* hp, cand_t c)
+{
+    cand_t* h = hp->h;
+    if (hp->n < hp->cap) {
+        uint32_t i = hp->n++;
+        while (i > 0) {
+            uint32_t p = (i - 1) / 2;
+            if (!better(h[p], c))
+                break;
+            h[i] = h[p];
+            i = p;
+        }
+        h[i] = c;
+        return;
+    }
+    if (hp->cap == 0 || !better(c, h[0]))
+        return;
+    uint32_t i = 0;
+    for (;;) {
+        uint32_t l = 2 * i + 1, r = l + 1, w = i;
+        cand_t worst = c;
+        if (l < hp->n && better(worst, h[l])) { w = l; worst = h[l]; }
+        if (r < hp->n && better(worst, h[r])) { w = r; worst = h[r]; }
+        if (w == i)
+            break;
+        h[i] = h[w];
+        i = w;
+    }
+    h[i] = c;
+}
+
+static int cmp_canonical(const void* a, const void* b)
+{
+    const cand_t x = *(const cand_t*) a, y = *(const cand_t*) b;
+    return better(x, y) ? -1 : (better(y, x) ? 1 : 0);
+}
+
+typedef struct {
+    const int32_t* q;
+    const int32_t* db;
+    int words;
+    uint64_t lo, hi, row_base;
+    float cutoff;
+    float* scores_out; /* optional: raw CPU scores */
+    heap_t heap;
+    uint64_t survivors;
+} job_t;
+
+static void* scan_job(void* arg)
+{
+    job_t* j = (job_t*) arg;
+    const int drop_zero = j->cutoff > 0.0f; /* .cu:265 */
+    for (uint64_t r = j->lo; r < j->hi; r++) {
+        float s = score_row(j->q, j->db + r * (uint64_t) j->words, j->words);
+        if (j->scores_out)
+            j->scores_out[r] = s;
+        if (!j->heap.cap && !drop_zero)
+            continue;
+        s = (s >= j->cutoff) ? s : 0.0f; /* .cu:102; NaN -> 0 */
+        if (drop_zero && s == 0.0f)
+            continue;
+        j->survivors++;
+        cand_t c = {s, (uint32_t) (r + j->row_base)};
+        heap_push(&j->heap, c);
+    }
+    return NULL;
+}
+
+static int run_jobs(const int32_t* q, int words, const int32_t* db, uint64_t n_rows,
+                    uint64_t row_base, uint32_t k, float cutoff, float* scores_out,
+                    int n_threads, cand_t** merged, uint32_t* n_merged, uint64_t* survivors)
+{
+    if (n_threads < 1)
+        n_threads = 1;
+    job_t* jobs = (job_t*) calloc(n_threads, sizeof(job_t));
+    pthread_t* th = (pthread_t*) calloc(n_threads, sizeof(pthread_t));
+    const uint64_t per = (n_rows + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        job_t* j = &jobs[t];
+        j->q = q; j->db = db; j->words = words; j->row_base = row_base;
+        j->lo = (uint64_t) t * per < n_rows ? (uint64_t) t * per : n_rows;
+        j->hi = j->lo + per < n_rows ? j->lo + per : n_rows;
+        j->cutoff = cutoff; j->scores_out = scores_out;
+        j->heap.cap = k; j->heap.n = 0;
+        j->heap.h = k ? (cand_t*) malloc((size_t) k * sizeof(cand_t)) : NULL;
+        pthread_create(&th[t], NULL, scan_job, j);
+    }
+    uint64_t surv = 0;
+    uint32_t total = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        surv += jobs[t].survivors;
+        total += jobs[t].heap.n;
+    }
+    cand_t* all = (cand_t*) malloc((size_t) (total ? total : 1) * sizeof(cand_t));
+    uint32_t o = 0;
+    for (int t = 0; t < n_threads; t++) {
+        memcpy(all + o, jobs[t].heap.h, (size_t) jobs[t].heap.n * sizeof(cand_t));
+        o += jobs[t].heap.n;
+        free(jobs[t].heap.h);
+    }
+    qsort(all, total, sizeof(cand_t), cmp_canonical);
+    *merged = all; *n_merged = total; *survivors = surv;
+    free(jobs); free(th);
+    return 0;
+}
+
+/* Raw CPU scores for every row (TanimotoFunctorCPU semantics: no cutoff, 0/0 = NaN). */
+void oracle_score(const int32_t* query, int words, const int32_t* db, uint64_t n_rows,
+                  float* out_scores, int n_threads)
+{
+    cand_t* m; uint32_t nm; uint64_t s;
+    run_jobs(query, words, db, n_rows, 0, 0, -1.0f, out_scores, n_threads, &m, &nm, &s);
+    free(m);
+}
+
+/* FingerprintDB::search semantics (unfolded): returns min(k, survivors) results in canonical
+ * order with global row ids, and the approximate (survivor) count. */
+void oracle_search(const int32_t* query, int words, const int32_t* db, uint64_t n_rows,
+                   uint64_t row_base, uint32_t k, float cutoff, uint32_t* out_rows,
+                   float* out_scores, uint32_t* out_n, uint64_t* out_approx, int n_threads)
+{
+    cand_t* m; uint32_t nm; uint64_t surv;
+    run_jobs(query, words, db, n_rows, row_base, k, cutoff, NULL, n_threads, &m, &nm, &surv);
+    const uint32_t n = nm < k ? nm : k;
+    for (uint32_t i = 0; i < n; i++) {
+        out_rows[i] = m[i].row;
+        out_scores[i] = m[i].score;
+    }
+    *out_n = n;
+    *out_approx = cutoff > 0.0f ? surv : n_rows; /* .cu:272-277, 367-369 */
+    free(m);
+}
+
+/* FoldFingerprintFunctorCPU (calculation_functors.cpp:22-41): OR of the `factor` contiguous
+ * segments of words/factor words. */
+void oracle_fold(const int32_t* fp, int words, int factor, int32_t* out)
+{
+    const int new_words = words / factor;
+    memset(out, 0, (size_t) new_words * sizeof(int32_t));
+    for (int w = 0; w < words; w++)
+        out[w % new_words] |= fp[w];
+}
