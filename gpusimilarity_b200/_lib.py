@@ -1,0 +1,82 @@
+"""ctypes binding of the C ABI in include/gpusim_b200.h (libgpusim_b200.so, built in-tree by
+``make`` / ``__graft_entry__.build()``).  There is no Python or CPU fallback: if the shared
+library is missing every entry point raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgpusim_b200.so")
+
+GSB_OK, GSB_ERR_INVALID, GSB_ERR_CUDA, GSB_ERR_NOMEM, GSB_ERR_STATE, GSB_ERR_CORRUPT, GSB_ERR_IO = range(7)
+
+
+class GsbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gpusim_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ScanInfo(C.Structure):
+    _fields_ = [("device", C.c_int), ("grid", C.c_int), ("block", C.c_int), ("stages", C.c_int),
+                ("tile_rows", C.c_uint32), ("tile_bytes", C.c_uint32), ("smem_bytes", C.c_uint32),
+                ("cand_capacity", C.c_uint32), ("shard_rows", C.c_uint64),
+                ("db_bytes_per_query", C.c_uint64)]
+
+
+# name -> (restype, argtypes); must list every symbol the header declares (tests check it)
+_P = C.c_void_p
+SIGNATURES = {
+    "gsb_last_error": (C.c_char_p, []),
+    "gsb_version": (C.c_char_p, []),
+    "gsb_device_count": (C.c_int, []),
+    "gsb_device_free_bytes": (C.c_uint64, [C.c_int]),
+    "gsb_available_device_bytes": (C.c_uint64, []),
+    "gsb_next_device": (C.c_int, [C.c_uint64, C.POINTER(C.c_int)]),
+    "gsb_db_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint64,
+                                C.POINTER(_P)]),
+    "gsb_db_create_synthetic": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                                          C.c_uint32, C.POINTER(_P)]),
+    "gsb_db_upload": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.c_uint]),
+    "gsb_db_destroy": (None, [_P]),
+    "gsb_db_count": (C.c_uint64, [_P]),
+    "gsb_db_fp_bits": (C.c_int, [_P]),
+    "gsb_db_data_bytes": (C.c_uint64, [_P]),
+    "gsb_db_fold_factor": (C.c_uint, [_P]),
+    "gsb_db_shard_count": (C.c_int, [_P]),
+    "gsb_db_get_fingerprint": (C.c_int, [_P, C.c_uint64, _P]),
+    "gsb_db_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_float, _P, _P,
+                                C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "gsb_db_search_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint32, C.c_float, _P, _P, _P, _P]),
+    "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
+    "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
+    "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "gsb_fold_fingerprint": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "gsb_db_scan_info": (C.c_int, [_P, C.c_int, C.c_uint32, C.POINTER(ScanInfo)]),
+    "gsb_launch_count": (C.c_uint64, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library.  Raises ImportError (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make` or `python -c 'import __graft_entry__ as g; "
+                "g.build()'`.  gpusimilarity_b200 has no fallback path.")
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != GSB_OK:
+        raise GsbError(rc, lib().gsb_last_error().decode())

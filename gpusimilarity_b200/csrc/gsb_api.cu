@@ -1,0 +1,954 @@
+// Host side of the C ABI declared in include/gpusim_b200.h: database life cycle, HBM layout,
+// launch planning and result marshalling around the kernels in gsb_kernels.cuh.
+//
+// Reference interfaces replaced (see the header for the per-function map):
+//   FingerprintDB ctor / copyToGPU / search / search_storage / getFingerprint
+//   (fingerprintdb_cuda.cu:117-381), search_cpu / fold_data (fingerprintdb_cuda.cpp:20-69),
+//   get_gpu_count / get_next_gpu / get_available_gpu_memory (fingerprintdb_cuda.cu:33-68,401-413).
+#include "gsb_kernels.cuh"
+
+#include "../../include/gpusim_b200.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace
+{
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define GSB_CUDA(expr)                                                                           \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail(GSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+int env_int(const char* name, int dflt)
+{
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+uint32_t pow2ceil(uint64_t v)
+{
+    uint32_t p = 1;
+    while (p < v)
+        p <<= 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------ HBM layout
+// The database lives in HBM as fixed-size tiles so that one TMA bulk copy moves one tile:
+//   tile t = rows [t*tile_rows, (t+1)*tile_rows), row-major, dev_words 32-bit words per row,
+//            then (rowpop layout only) tile_rows u16 row popcounts.
+// Without the trailer the tiles are back to back, i.e. the plain row-major matrix.
+struct Layout {
+    uint32_t words = 0;      // logical words per row (after folding)
+    uint32_t dev_words = 0;  // words per row in HBM: power of two in [4, 128], zero padded
+    uint32_t tile_rows = 0;
+    uint32_t row_bytes = 0;
+    uint32_t tile_bytes = 0;  // bytes per bulk copy
+    uint32_t tile_stride = 0; // distance between tiles
+    uint32_t stage_bytes = 0; // ring slot
+    bool rowpop = false;
+};
+
+int make_layout(uint32_t words, Layout* out)
+{
+    Layout l;
+    l.words = words;
+    l.dev_words = std::max<uint32_t>(4, pow2ceil(words));
+    if (l.dev_words > gsb::kMaxWords)
+        return fail(GSB_ERR_INVALID, "fingerprints wider than 4096 bits are not supported");
+    l.row_bytes = l.dev_words * 4;
+    const uint32_t tile_target = static_cast<uint32_t>(env_int("GSB_TILE_BYTES", 32768));
+    uint32_t rows = std::max<uint32_t>(32, tile_target / l.row_bytes);
+    rows = rows / 32 * 32;
+    l.tile_rows = rows;
+    l.rowpop = env_int("GSB_ROWPOP", 0) != 0;
+    l.tile_bytes = rows * l.row_bytes + (l.rowpop ? rows * 2 : 0);
+    l.tile_stride = l.tile_bytes; // multiple of 16: rows % 32 == 0
+    l.stage_bytes = (l.tile_bytes + 127) / 128 * 128;
+    *out = l;
+    return GSB_OK;
+}
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    gsb::ScanCtrl* ctrl = nullptr;
+    unsigned long long* cta_keys = nullptr;
+    uint32_t* cta_counts = nullptr;
+    uint64_t cta_keys_cap = 0; // entries
+    // results of the host-buffer API: [k keys][survivors u64][n u32]
+    unsigned long long* out_dev = nullptr;
+    unsigned long long* out_host = nullptr; // pinned
+    uint32_t out_cap = 0;                   // keys
+    int max_grid = 0;
+};
+
+struct Shard {
+    int device = 0;
+    uint64_t row_base = 0;
+    uint64_t n_rows = 0;
+    uint32_t n_tiles = 0;
+    uint8_t* tiles = nullptr;
+    size_t bytes = 0;
+    Workspace ws;
+};
+
+struct Plan {
+    int grid = 0;
+    uint32_t stages = 0, cap = 0, smem = 0;
+};
+
+} // namespace
+
+struct gsb_db {
+    int fp_bits = 0;
+    uint32_t words = 0; // unfolded words per row
+    uint64_t count = 0;
+    std::vector<uint32_t> host; // unfolded rows, row-major (empty for device-generated shards)
+    unsigned fold_factor = 1;
+    Layout layout;
+    std::vector<Shard> shards;
+    bool uploaded = false;
+    uint64_t synth_seed = 0;
+    mutable std::mutex mu; // one search in flight per database, like the reference
+};
+
+namespace
+{
+
+int smem_limit(int device, int* out)
+{
+    int v = 0;
+    GSB_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    *out = v;
+    return GSB_OK;
+}
+
+template <int W, bool RP> int set_smem_attr(int bytes)
+{
+    GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    return GSB_OK;
+}
+
+template <int W, bool RP> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
+{
+    static thread_local int configured[64] = {0};
+    int dev = 0;
+    GSB_CUDA(cudaGetDevice(&dev));
+    if (dev < 64 && configured[dev] < static_cast<int>(plan.smem)) {
+        int rc = set_smem_attr<W, RP>(plan.smem);
+        if (rc)
+            return rc;
+        configured[dev] = plan.smem;
+    }
+    gsb::scan_topk_kernel<W, RP><<<plan.grid, gsb::kThreads, plan.smem, st>>>(p);
+    g_launches++;
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+int launch_scan(const Layout& l, const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
+{
+#define GSB_CASE(W)                                                                              \
+    case W:                                                                                      \
+        return l.rowpop ? launch_scan_t<W, true>(p, plan, st) : launch_scan_t<W, false>(p, plan, st);
+    switch (l.dev_words) {
+        GSB_CASE(4)
+        GSB_CASE(8)
+        GSB_CASE(16)
+        GSB_CASE(32)
+        GSB_CASE(64)
+        GSB_CASE(128)
+    default:
+        return fail(GSB_ERR_INVALID, "unsupported device row width");
+    }
+#undef GSB_CASE
+}
+
+// Ring depth and candidate capacity for this k.  Rules the kernel relies on:
+//   cap is a power of two, cap >= k + 2*stages*tile_rows (room between two compactions and for
+//   the tiles in flight when one is requested) and cap >= k + grid (final merge rounds).
+int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
+{
+    int smem_max = 0;
+    int rc = smem_limit(sh.device, &smem_max);
+    if (rc)
+        return rc;
+    const int budget = smem_max - 2048; // static shared memory + alignment slack
+    int grid = sh.ws.max_grid;
+    if (const int g = env_int("GSB_GRID", 0))
+        grid = g;
+    grid = std::max(1, std::min<int>(grid, sh.n_tiles ? sh.n_tiles : 1));
+    const int want = std::min(gsb::kMaxStages, std::max(2, env_int("GSB_STAGES", 4)));
+    for (int st = want; st >= 2; st--) {
+        const uint64_t need = static_cast<uint64_t>(k) + 2ull * st * l.tile_rows;
+        const uint32_t cap = std::max<uint32_t>(pow2ceil(std::max<uint64_t>(need, k + (uint64_t) grid)),
+                                                static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));
+        const uint64_t smem = static_cast<uint64_t>(st) * l.stage_bytes + static_cast<uint64_t>(cap) * 8;
+        if (smem <= static_cast<uint64_t>(budget)) {
+            out->grid = grid;
+            out->stages = st;
+            out->cap = cap;
+            out->smem = static_cast<uint32_t>(smem);
+            return GSB_OK;
+        }
+    }
+    return fail(GSB_ERR_INVALID, "max_return_count " + std::to_string(k) +
+                                     " is too large for the fused in-kernel select");
+}
+
+int ws_init(Shard& sh)
+{
+    Workspace& ws = sh.ws;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    GSB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
+    GSB_CUDA(cudaMalloc(&ws.ctrl, sizeof(gsb::ScanCtrl)));
+    GSB_CUDA(cudaMemset(ws.ctrl, 0, sizeof(gsb::ScanCtrl)));
+    int sms = 0;
+    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+    ws.max_grid = sms * std::max(1, env_int("GSB_CTAS_PER_SM", 1));
+    GSB_CUDA(cudaMalloc(&ws.cta_counts, sizeof(uint32_t) * 4096));
+    return GSB_OK;
+}
+
+int ws_reserve(Shard& sh, uint32_t k, int grid, bool host_results)
+{
+    Workspace& ws = sh.ws;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    const uint64_t need = static_cast<uint64_t>(grid) * std::max<uint32_t>(k, 1);
+    if (need > ws.cta_keys_cap) {
+        if (ws.cta_keys)
+            GSB_CUDA(cudaFree(ws.cta_keys));
+        ws.cta_keys = nullptr;
+        GSB_CUDA(cudaMalloc(&ws.cta_keys, need * 8));
+        ws.cta_keys_cap = need;
+    }
+    if (host_results && k > ws.out_cap) {
+        if (ws.out_dev)
+            GSB_CUDA(cudaFree(ws.out_dev));
+        if (ws.out_host)
+            GSB_CUDA(cudaFreeHost(ws.out_host));
+        ws.out_dev = ws.out_host = nullptr;
+        const uint32_t cap = pow2ceil(std::max<uint32_t>(k, 1024));
+        GSB_CUDA(cudaMalloc(&ws.out_dev, (static_cast<size_t>(cap) + 2) * 8));
+        GSB_CUDA(cudaMallocHost(&ws.out_host, (static_cast<size_t>(cap) + 2) * 8));
+        ws.out_cap = cap;
+    }
+    return GSB_OK;
+}
+
+void ws_free(Shard& sh)
+{
+    cudaSetDevice(sh.device);
+    Workspace& ws = sh.ws;
+    if (ws.stream)
+        cudaStreamDestroy(ws.stream);
+    cudaFree(ws.ctrl);
+    cudaFree(ws.cta_keys);
+    cudaFree(ws.cta_counts);
+    cudaFree(ws.out_dev);
+    if (ws.out_host)
+        cudaFreeHost(ws.out_host);
+    cudaFree(sh.tiles);
+    sh = Shard();
+}
+
+// FoldFingerprintFunctorCPU (reference calculation_functors.cpp:22-41): bit pos -> pos % new
+// size with the in-word position kept, i.e. OR of `factor` contiguous word segments.
+void fold_row(const uint32_t* in, uint32_t words, uint32_t factor, uint32_t* out)
+{
+    const uint32_t nw = words / factor;
+    for (uint32_t w = 0; w < nw; w++)
+        out[w] = 0;
+    for (uint32_t w = 0; w < words; w++)
+        out[w % nw] |= in[w];
+}
+
+void parallel_for(uint64_t n, const std::function<void(uint64_t, uint64_t)>& fn)
+{
+    unsigned nt = std::max(1u, std::thread::hardware_concurrency());
+    if (const int e = env_int("GSB_HOST_THREADS", 0))
+        nt = e;
+    if (n < 65536 || nt == 1) {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const uint64_t per = (n + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const uint64_t lo = std::min(n, t * per), hi = std::min(n, lo + per);
+        if (lo >= hi)
+            break;
+        pool.emplace_back([&fn, lo, hi]() { fn(lo, hi); });
+    }
+    for (auto& th : pool)
+        th.join();
+}
+
+// Copy rows [row0, row0+n) of the (possibly folded/padded) host matrix into a shard's tiles.
+int upload_rows(const gsb_db* db, Shard& sh)
+{
+    const Layout& l = db->layout;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    sh.n_tiles = static_cast<uint32_t>((sh.n_rows + l.tile_rows - 1) / l.tile_rows);
+    sh.bytes = static_cast<size_t>(std::max<uint32_t>(sh.n_tiles, 1)) * l.tile_stride;
+    if (gsb_device_free_bytes(sh.device) <= sh.bytes)
+        return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
+    GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
+    GSB_CUDA(cudaMemsetAsync(sh.tiles, 0, sh.bytes, sh.ws.stream));
+
+    const uint32_t src_words = db->words;
+    const bool direct = db->fold_factor == 1 && l.dev_words == src_words;
+    const uint32_t* src = nullptr;
+    std::vector<uint32_t> staged;
+    if (direct) {
+        src = db->host.data() + sh.row_base * src_words;
+    } else {
+        staged.assign(static_cast<size_t>(sh.n_rows) * l.dev_words, 0u);
+        const uint32_t f = db->fold_factor;
+        const uint32_t* base = db->host.data() + sh.row_base * src_words;
+        uint32_t* dst = staged.data();
+        const uint32_t dw = l.dev_words, fw = src_words / f;
+        parallel_for(sh.n_rows, [=](uint64_t lo, uint64_t hi) {
+            std::vector<uint32_t> tmp(fw);
+            for (uint64_t r = lo; r < hi; r++) {
+                fold_row(base + r * src_words, src_words, f, tmp.data());
+                std::memcpy(dst + r * dw, tmp.data(), fw * 4);
+            }
+        });
+        src = staged.data();
+    }
+    const size_t tile_row_bytes = static_cast<size_t>(l.tile_rows) * l.row_bytes;
+    if (!l.rowpop) {
+        GSB_CUDA(cudaMemcpyAsync(sh.tiles, src, static_cast<size_t>(sh.n_rows) * l.row_bytes,
+                                 cudaMemcpyHostToDevice, sh.ws.stream));
+    } else {
+        const uint64_t full = sh.n_rows / l.tile_rows;
+        if (full)
+            GSB_CUDA(cudaMemcpy2DAsync(sh.tiles, l.tile_stride, src, tile_row_bytes, tile_row_bytes, full,
+                                       cudaMemcpyHostToDevice, sh.ws.stream));
+        const uint64_t rest = sh.n_rows - full * l.tile_rows;
+        if (rest)
+            GSB_CUDA(cudaMemcpyAsync(sh.tiles + full * l.tile_stride,
+                                     reinterpret_cast<const uint8_t*>(src) + full * tile_row_bytes,
+                                     rest * l.row_bytes, cudaMemcpyHostToDevice, sh.ws.stream));
+        const uint64_t rows = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows;
+        if (rows) {
+            gsb::tile_popcount_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, sh.ws.stream>>>(
+                sh.tiles, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words);
+            g_launches++;
+        }
+    }
+    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k, float cutoff,
+                 gsb::ScanParams* p)
+{
+    const Layout& l = db->layout;
+    std::memset(p, 0, sizeof(*p));
+    p->tiles = sh.tiles;
+    p->n_rows = sh.n_rows;
+    p->row_base = sh.row_base;
+    p->n_tiles = sh.n_tiles;
+    p->tile_rows = l.tile_rows;
+    p->tile_stride = l.tile_stride;
+    p->tile_bytes = l.tile_bytes;
+    p->stage_bytes = l.stage_bytes;
+    p->stages = plan.stages;
+    p->cap = plan.cap;
+    p->k = k;
+    p->cutoff = cutoff;
+    p->cta_keys = sh.ws.cta_keys;
+    p->cta_counts = sh.ws.cta_counts;
+    p->ctrl = sh.ws.ctrl;
+}
+
+struct Cand {
+    float score;
+    uint32_t row;
+};
+
+inline Cand decode(unsigned long long key)
+{
+    Cand c;
+    const uint32_t bits = static_cast<uint32_t>(key >> 32);
+    std::memcpy(&c.score, &bits, 4);
+    c.row = 0xffffffffu - static_cast<uint32_t>(key & 0xffffffffu);
+    return c;
+}
+
+// One scan per shard with a host-resident query; leaves keys/n/survivors in ws.out_host.
+int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, float cutoff,
+                    std::vector<unsigned long long>* keys, uint64_t* survivors)
+{
+    std::vector<Plan> plans(db->shards.size());
+    for (size_t i = 0; i < db->shards.size(); i++) {
+        Shard& sh = const_cast<Shard&>(db->shards[i]);
+        if (sh.n_rows == 0)
+            continue;
+        int rc = make_plan(db->layout, sh, k, &plans[i]);
+        if (rc)
+            return rc;
+        rc = ws_reserve(sh, k, plans[i].grid, true);
+        if (rc)
+            return rc;
+        GSB_CUDA(cudaSetDevice(sh.device));
+        gsb::ScanParams p;
+        fill_params(db, sh, plans[i], k, cutoff, &p);
+        std::memcpy(p.q_host, q_dev_words, db->layout.dev_words * 4);
+        p.out_keys = sh.ws.out_dev;
+        p.out_survivors = sh.ws.out_dev + k;
+        p.out_n = reinterpret_cast<uint32_t*>(sh.ws.out_dev + k + 1);
+        rc = launch_scan(db->layout, p, plans[i], sh.ws.stream);
+        if (rc)
+            return rc;
+        GSB_CUDA(cudaMemcpyAsync(sh.ws.out_host, sh.ws.out_dev, (static_cast<size_t>(k) + 2) * 8,
+                                 cudaMemcpyDeviceToHost, sh.ws.stream));
+    }
+    keys->clear();
+    *survivors = 0;
+    for (size_t i = 0; i < db->shards.size(); i++) {
+        const Shard& sh = db->shards[i];
+        if (sh.n_rows == 0)
+            continue;
+        GSB_CUDA(cudaSetDevice(sh.device));
+        GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+        const uint32_t n = *reinterpret_cast<const uint32_t*>(sh.ws.out_host + k + 1);
+        *survivors += sh.ws.out_host[k];
+        if (db->shards.size() == 1) {
+            keys->assign(sh.ws.out_host, sh.ws.out_host + n);
+        } else {
+            // merge of per-shard sorted lists on the host (reference .cu:366 sorts on the host too)
+            const size_t old = keys->size();
+            keys->insert(keys->end(), sh.ws.out_host, sh.ws.out_host + n);
+            std::inplace_merge(keys->begin(), keys->begin() + old, keys->end(),
+                               std::greater<unsigned long long>());
+            if (keys->size() > k)
+                keys->resize(k);
+        }
+    }
+    return GSB_OK;
+}
+
+void to_dev_words(const gsb_db* db, const int32_t* query, std::vector<uint32_t>* out)
+{
+    out->assign(db->layout.dev_words, 0u);
+    if (db->fold_factor == 1) {
+        std::memcpy(out->data(), query, db->words * 4);
+    } else {
+        fold_row(reinterpret_cast<const uint32_t*>(query), db->words, db->fold_factor, out->data());
+    }
+}
+
+float score_cpu(const uint32_t* q, const uint32_t* d, uint32_t words)
+{
+    // reference calculation_functors.cpp:8-19 / fingerprintdb_cuda.cu:387-399
+    int total = 0, common = 0;
+    for (uint32_t i = 0; i < words; i++) {
+        total += __builtin_popcount(q[i]) + __builtin_popcount(d[i]);
+        common += __builtin_popcount(q[i] & d[i]);
+    }
+    return static_cast<float>(common) / static_cast<float>(total - common);
+}
+
+int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<uint32_t>* out);
+
+} // namespace
+
+// ====================================================================================== C ABI
+extern "C" {
+
+const char* gsb_last_error(void) { return g_err.c_str(); }
+const char* gsb_version(void) { return "gpusim_b200 0.1 (sm_100a)"; }
+uint64_t gsb_launch_count(void) { return g_launches.load(); }
+
+int gsb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+uint64_t gsb_device_free_bytes(int device)
+{
+    size_t free_b = 0, total = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&free_b, &total) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    cudaSetDevice(cur);
+    return free_b;
+}
+
+uint64_t gsb_available_device_bytes(void)
+{
+    uint64_t sum = 0;
+    for (int d = 0; d < gsb_device_count(); d++)
+        sum += gsb_device_free_bytes(d);
+    return sum;
+}
+
+int gsb_next_device(uint64_t required_bytes, int* device)
+{
+    static std::atomic<unsigned> next{0};
+    const int n = gsb_device_count();
+    if (n == 0)
+        return fail(GSB_ERR_CUDA, "no CUDA device");
+    for (int i = 0; i < n; i++) {
+        const int gpu = static_cast<int>(next++ % static_cast<unsigned>(n));
+        if (gsb_device_free_bytes(gpu) > required_bytes) {
+            *device = gpu;
+            return GSB_OK;
+        }
+    }
+    return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
+}
+
+int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, int n_chunks,
+                  int fp_bits, uint64_t fp_count, gsb_db** out)
+{
+    if (!out || n_chunks < 0 || (n_chunks > 0 && (!chunk_ptrs || !chunk_bytes)))
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
+        return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
+    const uint64_t row_bytes = fp_bits / 8;
+    uint64_t total = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        if (chunk_bytes[c] % row_bytes != 0)
+            return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
+        total += chunk_bytes[c] / row_bytes;
+    }
+    if (total != fp_count) // reference fingerprintdb_cuda.cu:153-156
+        return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
+    std::unique_ptr<gsb_db> db(new gsb_db);
+    db->fp_bits = fp_bits;
+    db->words = fp_bits / 32;
+    db->count = fp_count;
+    db->host.resize(fp_count * db->words);
+    uint64_t off = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        std::memcpy(reinterpret_cast<uint8_t*>(db->host.data()) + off, chunk_ptrs[c], chunk_bytes[c]);
+        off += chunk_bytes[c];
+    }
+    *out = db.release();
+    return GSB_OK;
+}
+
+int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base, uint64_t seed,
+                            uint32_t plant_period, gsb_db** out)
+{
+    if (!out)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
+        return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
+    if (row_base + n_rows > 0xffffffffull)
+        return fail(GSB_ERR_INVALID, "row ids must fit 32 bits");
+    if (device < 0 || device >= gsb_device_count())
+        return fail(GSB_ERR_CUDA, "no such CUDA device");
+    std::unique_ptr<gsb_db> db(new gsb_db);
+    db->fp_bits = fp_bits;
+    db->words = fp_bits / 32;
+    db->count = n_rows;
+    db->synth_seed = seed;
+    int rc = make_layout(db->words, &db->layout);
+    if (rc)
+        return rc;
+    if (db->layout.dev_words != db->words)
+        return fail(GSB_ERR_INVALID, "synthetic shards need a power-of-two word count >= 4");
+    db->shards.resize(1);
+    Shard& sh = db->shards[0];
+    sh.device = device;
+    sh.row_base = row_base;
+    sh.n_rows = n_rows;
+    rc = ws_init(sh);
+    if (rc)
+        return rc;
+    const Layout& l = db->layout;
+    sh.n_tiles = static_cast<uint32_t>((n_rows + l.tile_rows - 1) / l.tile_rows);
+    sh.bytes = static_cast<size_t>(std::max<uint32_t>(sh.n_tiles, 1)) * l.tile_stride;
+    if (gsb_device_free_bytes(device) <= sh.bytes)
+        return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
+    GSB_CUDA(cudaSetDevice(device));
+    GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
+    const uint64_t n_words = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows * l.dev_words;
+    if (n_words) {
+        const uint64_t blocks = (n_words + 255) / 256;
+        if (blocks > 0x7fffffffull)
+            return fail(GSB_ERR_INVALID, "shard too large");
+        gsb::synth_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, sh.ws.stream>>>(
+            sh.tiles, n_rows, row_base, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words, seed, plant_period);
+        g_launches++;
+        if (l.rowpop) {
+            const uint64_t rows = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows;
+            gsb::tile_popcount_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, sh.ws.stream>>>(
+                sh.tiles, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words);
+            g_launches++;
+        }
+    }
+    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+    GSB_CUDA(cudaGetLastError());
+    db->uploaded = true;
+    *out = db.release();
+    return GSB_OK;
+}
+
+int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_factor)
+{
+    if (!db)
+        return fail(GSB_ERR_INVALID, "null database");
+    std::lock_guard<std::mutex> lock(db->mu);
+    if (db->host.empty() && db->count > 0)
+        return fail(GSB_ERR_STATE, "device-generated shards are already uploaded");
+    const int n_vis = gsb_device_count();
+    if (n_vis == 0)
+        return fail(GSB_ERR_CUDA, "no CUDA device: the GPU search path has no CPU fallback");
+    for (auto& sh : db->shards)
+        ws_free(sh);
+    db->shards.clear();
+    db->uploaded = false;
+    // reference fingerprintdb_cuda.cu:170-173
+    unsigned f = std::max(1u, fold_factor);
+    while (db->words % f != 0)
+        f++;
+    db->fold_factor = f;
+    int rc = make_layout(db->words / f, &db->layout);
+    if (rc)
+        return rc;
+    std::vector<int> devs;
+    if (devices && n_devices > 0) {
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= n_vis)
+                return fail(GSB_ERR_INVALID, "no such CUDA device");
+            devs.push_back(devices[i]);
+        }
+    } else {
+        // as many devices as needed: keep shards >= 1 GiB so tiny databases stay on one GPU
+        const uint64_t bytes = db->count * db->layout.row_bytes;
+        const int want = static_cast<int>(std::min<uint64_t>(n_vis, std::max<uint64_t>(1, bytes >> 30)));
+        for (int i = 0; i < want; i++) {
+            int d = 0;
+            rc = gsb_next_device(0, &d);
+            if (rc)
+                return rc;
+            devs.push_back(d);
+        }
+    }
+    const uint64_t per = (db->count + devs.size() - 1) / devs.size();
+    db->shards.resize(devs.size());
+    for (size_t i = 0; i < devs.size(); i++) {
+        Shard& sh = db->shards[i];
+        sh.device = devs[i];
+        sh.row_base = std::min<uint64_t>(db->count, i * per);
+        sh.n_rows = std::min<uint64_t>(db->count - sh.row_base, per);
+        rc = ws_init(sh);
+        if (rc)
+            return rc;
+        rc = upload_rows(db, sh);
+        if (rc)
+            return rc;
+    }
+    db->uploaded = true;
+    return GSB_OK;
+}
+
+void gsb_db_destroy(gsb_db* db)
+{
+    if (!db)
+        return;
+    for (auto& sh : db->shards)
+        ws_free(sh);
+    delete db;
+}
+
+uint64_t gsb_db_count(const gsb_db* db) { return db ? db->count : 0; }
+int gsb_db_fp_bits(const gsb_db* db) { return db ? db->fp_bits : 0; }
+uint64_t gsb_db_data_bytes(const gsb_db* db) { return db ? db->count * db->words * 4ull : 0; }
+unsigned gsb_db_fold_factor(const gsb_db* db) { return db ? db->fold_factor : 0; }
+int gsb_db_shard_count(const gsb_db* db) { return db ? static_cast<int>(db->shards.size()) : 0; }
+
+int gsb_db_get_fingerprint(const gsb_db* db, uint64_t row, int32_t* out_words)
+{
+    if (!db || !out_words)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (row >= db->count)
+        return fail(GSB_ERR_INVALID, "row out of range");
+    if (!db->host.empty()) {
+        std::memcpy(out_words, db->host.data() + row * db->words, db->words * 4);
+        return GSB_OK;
+    }
+    std::vector<uint32_t> tmp;
+    int rc = fetch_rows(db, {row}, &tmp);
+    if (rc)
+        return rc;
+    std::memcpy(out_words, tmp.data(), db->words * 4);
+    return GSB_OK;
+}
+
+int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k, float cutoff,
+                  uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+{
+    if (!db || !query_words || !out_n || (k > 0 && (!out_rows || !out_scores)))
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (n_words != static_cast<int>(db->words))
+        return fail(GSB_ERR_INVALID, "query width does not match the database");
+    if (gsb_device_count() == 0)
+        return fail(GSB_ERR_CUDA, "no CUDA device: the GPU search path has no CPU fallback");
+    if (!db->uploaded)
+        return fail(GSB_ERR_STATE, "database is not on the GPU: call gsb_db_upload first");
+    std::lock_guard<std::mutex> lock(db->mu);
+    std::vector<uint32_t> q;
+    to_dev_words(db, query_words, &q);
+    const unsigned f = db->fold_factor;
+    // reference .cu:284-287: candidates to pull back from the (folded) scan
+    uint64_t k_scan = k;
+    if (f > 1)
+        k_scan = static_cast<uint64_t>(k) * f * static_cast<uint64_t>(std::log2(2.0 * f));
+    k_scan = std::min<uint64_t>(k_scan, db->count);
+    std::vector<unsigned long long> keys;
+    uint64_t survivors = 0;
+    int rc = scan_all_shards(db, q.data(), static_cast<uint32_t>(std::max<uint64_t>(k_scan, 1)), cutoff, &keys,
+                             &survivors);
+    if (rc)
+        return rc;
+    if (keys.size() > k_scan)
+        keys.resize(k_scan);
+    if (out_approx)
+        *out_approx = survivors;
+    if (f == 1) {
+        const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(keys.size(), k));
+        for (uint32_t i = 0; i < n; i++) {
+            const Cand c = decode(keys[i]);
+            out_rows[i] = c.row;
+            out_scores[i] = c.score;
+        }
+        *out_n = n;
+        return GSB_OK;
+    }
+    // folded: re-score the candidates with the full fingerprints (reference .cu:307-331)
+    std::vector<Cand> cand(keys.size());
+    const uint32_t* qfull = reinterpret_cast<const uint32_t*>(query_words);
+    for (size_t i = 0; i < keys.size(); i++) {
+        cand[i].row = decode(keys[i]).row;
+        cand[i].score = score_cpu(qfull, db->host.data() + static_cast<uint64_t>(cand[i].row) * db->words, db->words);
+    }
+    // top_results_bubble_sort (.cpp:92-103) == stable descending sort of the candidate order
+    std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });
+    uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cand.size(), k));
+    for (uint32_t i = 0; i < n; i++) {
+        if (cand[i].score < cutoff) { // .cu:323-326
+            n = i;
+            break;
+        }
+        out_rows[i] = cand[i].row;
+        out_scores[i] = cand[i].score;
+    }
+    *out_n = n;
+    return GSB_OK;
+}
+
+int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words, int n_queries, uint32_t k,
+                        float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
+                        uint64_t* out_approx)
+{
+    if (n_queries < 0)
+        return fail(GSB_ERR_INVALID, "negative query count");
+    for (int qi = 0; qi < n_queries; qi++) {
+        int rc = gsb_db_search(db, query_words + static_cast<size_t>(qi) * n_words, n_words, k, cutoff,
+                               out_rows + static_cast<size_t>(qi) * k, out_scores + static_cast<size_t>(qi) * k,
+                               out_n + qi, out_approx ? out_approx + qi : nullptr);
+        if (rc)
+            return rc;
+    }
+    return GSB_OK;
+}
+
+int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k, uint32_t* out_rows,
+                      float* out_scores, uint32_t* out_n)
+{
+    if (!db || !query_words || !out_n || (k > 0 && (!out_rows || !out_scores)))
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (n_words != static_cast<int>(db->words))
+        return fail(GSB_ERR_INVALID, "query width does not match the database");
+    if (db->host.empty() && db->count > 0)
+        return fail(GSB_ERR_STATE, "search_cpu needs host-resident rows");
+    const uint32_t* q = reinterpret_cast<const uint32_t*>(query_words);
+    std::vector<float> scores(db->count);
+    const uint32_t words = db->words;
+    const uint32_t* rows = db->host.data();
+    float* sp = scores.data();
+    parallel_for(db->count, [=](uint64_t lo, uint64_t hi) {
+        for (uint64_t r = lo; r < hi; r++)
+            sp[r] = score_cpu(q, rows + r * words, words);
+    });
+    const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(k, db->count));
+    std::vector<uint32_t> idx(db->count);
+    for (uint64_t i = 0; i < db->count; i++)
+        idx[i] = static_cast<uint32_t>(i);
+    // first k of the stable descending order == the reference's partial bubble sort (NaN last)
+    auto better = [sp](uint32_t a, uint32_t b) {
+        const float x = sp[a], y = sp[b];
+        const bool xn = x != x, yn = y != y;
+        if (xn || yn)
+            return !xn && yn ? true : (xn && !yn ? false : a < b);
+        return x > y || (x == y && a < b);
+    };
+    std::partial_sort(idx.begin(), idx.begin() + n, idx.end(), better);
+    for (uint32_t i = 0; i < n; i++) {
+        out_rows[i] = idx[i];
+        out_scores[i] = sp[idx[i]];
+    }
+    *out_n = n;
+    return GSB_OK;
+}
+
+int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k, float cutoff,
+                         gsb_key* d_out_keys, uint32_t* d_out_n, uint64_t* d_out_survivors)
+{
+    if (!db || !d_query || !d_out_keys || !d_out_n || !d_out_survivors || k == 0)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (!db->uploaded || db->shards.size() != 1)
+        return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
+    if (db->fold_factor != 1)
+        return fail(GSB_ERR_STATE, "device search does not re-score folded databases");
+    Shard& sh = const_cast<Shard&>(db->shards[0]);
+    Plan plan;
+    int rc = make_plan(db->layout, sh, k, &plan);
+    if (rc)
+        return rc;
+    rc = ws_reserve(sh, k, plan.grid, false);
+    if (rc)
+        return rc;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    gsb::ScanParams p;
+    fill_params(db, sh, plan, k, cutoff, &p);
+    p.q_dev = reinterpret_cast<const uint32_t*>(d_query);
+    p.out_keys = reinterpret_cast<unsigned long long*>(d_out_keys);
+    p.out_n = d_out_n;
+    p.out_survivors = reinterpret_cast<unsigned long long*>(d_out_survivors);
+    return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
+}
+
+int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint32_t* d_counts, int n_lists,
+                     uint32_t list_stride, uint32_t k, uint32_t* d_out_rows, float* d_out_scores, uint32_t* d_out_n)
+{
+    if (!d_keys || !d_out_rows || !d_out_scores || !d_out_n || n_lists <= 0 || k == 0)
+        return fail(GSB_ERR_INVALID, "null argument");
+    GSB_CUDA(cudaSetDevice(device));
+    const uint32_t cap = std::max<uint32_t>(4096, pow2ceil(static_cast<uint64_t>(k) + 32ull * n_lists));
+    const size_t smem = static_cast<size_t>(cap) * 8;
+    int smem_max = 0;
+    int rc = smem_limit(device, &smem_max);
+    if (rc)
+        return rc;
+    if (smem + 1024 > static_cast<size_t>(smem_max))
+        return fail(GSB_ERR_INVALID, "k too large for the merge kernel");
+    GSB_CUDA(cudaFuncSetAttribute(gsb::merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    gsb::merge_kernel<<<1, gsb::kConsumerThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long*>(d_keys), d_counts, static_cast<uint32_t>(n_lists), list_stride,
+        k, cap, d_out_rows, d_out_scores, d_out_n);
+    g_launches++;
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
+}
+
+int gsb_fold_fingerprint(const int32_t* words, int n_words, int factor, int32_t* out_words)
+{
+    if (!words || !out_words || n_words <= 0 || factor <= 0 || n_words % factor != 0)
+        return fail(GSB_ERR_INVALID, "fold factor must divide the word count");
+    fold_row(reinterpret_cast<const uint32_t*>(words), n_words, factor, reinterpret_cast<uint32_t*>(out_words));
+    return GSB_OK;
+}
+
+int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out)
+{
+    if (!db || !out || shard < 0 || shard >= static_cast<int>(db->shards.size()))
+        return fail(GSB_ERR_INVALID, "bad shard");
+    const Shard& sh = db->shards[shard];
+    Plan plan;
+    int rc = make_plan(db->layout, sh, k, &plan);
+    if (rc)
+        return rc;
+    out->device = sh.device;
+    out->grid = plan.grid;
+    out->block = gsb::kThreads;
+    out->stages = plan.stages;
+    out->tile_rows = db->layout.tile_rows;
+    out->tile_bytes = db->layout.tile_bytes;
+    out->smem_bytes = plan.smem;
+    out->cand_capacity = plan.cap;
+    out->shard_rows = sh.n_rows;
+    out->db_bytes_per_query = static_cast<uint64_t>(sh.n_tiles) * db->layout.tile_bytes;
+    return GSB_OK;
+}
+
+} // extern "C"
+
+namespace
+{
+int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<uint32_t>* out)
+{
+    // rows are global ids; find the shard of each (device-generated databases have one shard)
+    const Layout& l = db->layout;
+    out->assign(rows.size() * db->words, 0u);
+    for (const Shard& sh : db->shards) {
+        std::vector<uint64_t> local;
+        std::vector<size_t> where;
+        for (size_t i = 0; i < rows.size(); i++) {
+            if (rows[i] >= sh.row_base && rows[i] < sh.row_base + sh.n_rows) {
+                local.push_back(rows[i] - sh.row_base);
+                where.push_back(i);
+            }
+        }
+        if (local.empty())
+            continue;
+        GSB_CUDA(cudaSetDevice(sh.device));
+        uint64_t* d_rows = nullptr;
+        uint32_t* d_out = nullptr;
+        GSB_CUDA(cudaMalloc(&d_rows, local.size() * 8));
+        GSB_CUDA(cudaMalloc(&d_out, local.size() * l.dev_words * 4));
+        GSB_CUDA(cudaMemcpy(d_rows, local.data(), local.size() * 8, cudaMemcpyHostToDevice));
+        const uint32_t n = static_cast<uint32_t>(local.size());
+        gsb::gather_rows_kernel<<<(n * l.dev_words + 255) / 256, 256>>>(sh.tiles, l.tile_rows, l.tile_stride,
+                                                                        l.dev_words, d_rows, n, d_out);
+        g_launches++;
+        std::vector<uint32_t> tmp(local.size() * l.dev_words);
+        GSB_CUDA(cudaMemcpy(tmp.data(), d_out, tmp.size() * 4, cudaMemcpyDeviceToHost));
+        cudaFree(d_rows);
+        cudaFree(d_out);
+        for (size_t i = 0; i < local.size(); i++)
+            std::memcpy(out->data() + where[i] * db->words, tmp.data() + i * l.dev_words, db->words * 4);
+    }
+    return GSB_OK;
+}
+} // namespace

@@ -1,0 +1,148 @@
+/* gpusim_b200.h — C ABI of the B200-native brute-force Tanimoto scan + top-k engine.
+ *
+ * This is the drop-in boundary for gpusimilarity's one hot path: everything that
+ * `gpusim::FingerprintDB` (reference fingerprintdb_cuda.h:53-147) asks of CUDA goes through
+ * these entry points.  Plain pointers and sizes only; no Qt, Thrust or torch types.
+ * Strings (SMILES / ids, the dbkey gate) never cross this boundary: the engine speaks
+ * GLOBAL ROW NUMBERS and the C++ adapter (include/gpusim/fingerprintdb_cuda.h) or the
+ * Python mirror (gpusimilarity_b200/fingerprintdb.py) maps rows back to strings.
+ *
+ * Result order is canonical: score descending, then global row ascending — what the
+ * reference's stable per-chunk sort produces (fingerprintdb_cuda.cu:245,280-282).
+ * Scores are bit-identical to `float(common) / float(total - common)` with an IEEE
+ * round-to-nearest divide (fingerprintdb_cuda.cu:100-101); `score >= cutoff ? score : 0`
+ * (:102) makes 0/0 rows score 0.
+ *
+ * Every function returns GSB_OK (0) or an error code; gsb_last_error() gives the message
+ * (thread-local).  There is NO CPU fallback behind the GPU entry points: without a usable
+ * CUDA device they fail with GSB_ERR_CUDA.
+ */
+#ifndef GPUSIM_B200_H
+#define GPUSIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSB_OK 0
+#define GSB_ERR_INVALID 1   /* bad argument (std::invalid_argument in the adapter)        */
+#define GSB_ERR_CUDA 2      /* CUDA runtime / device failure (reference: thrust::system_error) */
+#define GSB_ERR_NOMEM 3     /* no device with enough memory (reference .cu:65-66)          */
+#define GSB_ERR_STATE 4     /* call out of order, e.g. search before upload                */
+#define GSB_ERR_CORRUPT 5   /* row count does not match the data (reference .cu:153-156)   */
+#define GSB_ERR_IO 6        /* .fsim file could not be read / wrong version (gpusim.cpp:186-189) */
+
+#define GSB_MAX_WORDS 128   /* widest fingerprint: 4096 bits */
+
+typedef struct gsb_db gsb_db;
+
+/* ---- library / devices -------------------------------------------------------------- */
+const char* gsb_last_error(void);
+const char* gsb_version(void);
+/* reference get_gpu_count(), fingerprintdb_cuda.cu:41-52 */
+int gsb_device_count(void);
+/* reference get_gpu_free_memory(), fingerprintdb_cuda.cu:33-39 (0 on error) */
+uint64_t gsb_device_free_bytes(int device);
+/* reference get_available_gpu_memory(), fingerprintdb_cuda.cu:401-413 */
+uint64_t gsb_available_device_bytes(void);
+/* reference get_next_gpu(), fingerprintdb_cuda.cu:54-68: round-robin over devices, first one
+ * with more than required_bytes free (checks the device it returns — the reference checks a
+ * different one); GSB_ERR_NOMEM if none. */
+int gsb_next_device(uint64_t required_bytes, int* device);
+
+/* ---- database life cycle ------------------------------------------------------------ */
+/* reference FingerprintDB::FingerprintDB + FingerprintDBStorage ctor, .cu:117-166.
+ * chunk i holds chunk_bytes[i] bytes of packed rows (fp_bits/8 bytes each, whole rows).
+ * The bytes are copied (the reference copies them too, .cu:123-125).  fp_bits % 32 == 0.
+ * GSB_ERR_CORRUPT when the chunks do not add up to fp_count rows. */
+int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, int n_chunks,
+                  int fp_bits, uint64_t fp_count, gsb_db** out);
+/* A synthetic shard generated directly in device memory (benchmarks at sizes no host file
+ * can hold): rows [row_base, row_base + n_rows) of the counter-based database described in
+ * DESIGN.md ("Synthetic data"; host twin: oracle/oracle.py synth_rows).  Already uploaded. */
+int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base,
+                            uint64_t seed, uint32_t plant_period, gsb_db** out);
+/* reference FingerprintDB::copyToGPU, .cu:168-195.  Rows are split into contiguous, equal
+ * shards over `devices` (NULL / 0 = every visible device that is needed).  fold_factor is
+ * bumped to the next divisor of the word count (.cu:170-173); with fold_factor > 1 the
+ * folded rows are what is uploaded and searched (re-scored with the full rows kept on the host). */
+int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_factor);
+void gsb_db_destroy(gsb_db* db);
+
+uint64_t gsb_db_count(const gsb_db* db);          /* FingerprintDB::count(), .h:74            */
+int gsb_db_fp_bits(const gsb_db* db);             /* getFingerprintBitcount(), .h:124-127      */
+uint64_t gsb_db_data_bytes(const gsb_db* db);     /* getFingerprintDataSize(), .h:123          */
+unsigned gsb_db_fold_factor(const gsb_db* db);    /* effective factor after upload             */
+int gsb_db_shard_count(const gsb_db* db);
+/* reference FingerprintDB::getFingerprint, .cu:212-226 (without its chunk-boundary
+ * off-by-one).  out_words has fp_bits/32 entries. */
+int gsb_db_get_fingerprint(const gsb_db* db, uint64_t row, int32_t* out_words);
+
+/* ---- search ------------------------------------------------------------------------- */
+/* reference FingerprintDB::search, .cu:341-381 (+ search_storage :228-339).  HOST buffers in
+ * and out; one call = query upload, one fused scan+select launch per shard, merge, results
+ * back.  out_rows/out_scores hold k entries; *out_n = min(k, survivors) are written.
+ * *out_approx = rows with score >= cutoff when cutoff > 0, else the row count (:265-277). */
+int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k,
+                  float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
+                  uint64_t* out_approx);
+/* New (the reference serves one query per request, gpusim.cpp:407-414): n_queries queries
+ * over the same database; query q's results land at out_rows + q*k etc.  Identical results to
+ * n_queries calls of gsb_db_search. */
+int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words,
+                        int n_queries, uint32_t k, float cutoff, uint32_t* out_rows,
+                        float* out_scores, uint32_t* out_n, uint64_t* out_approx);
+/* reference FingerprintDB::search_cpu, fingerprintdb_cuda.cpp:20-54: host threads, CPU
+ * scores (no cutoff, 0/0 = NaN), first k in stable score-descending order.  A separate
+ * entry point of the reference API — never used as a fallback by gsb_db_search.
+ * Searches every chunk and clamps k to the row count (the reference does neither). */
+int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k,
+                      uint32_t* out_rows, float* out_scores, uint32_t* out_n);
+
+/* ---- device-resident entry points (one process per GPU; torch.distributed plumbing) ---- */
+/* Packed candidate: (float bits of score << 32) | (0xFFFFFFFF - global row).  Larger key =
+ * better in canonical order, so one unsigned compare orders candidates. */
+typedef uint64_t gsb_key;
+
+/* Asynchronous search of this process's single shard on `stream` (a cudaStream_t; NULL = the
+ * legacy default stream).  d_query: fp_bits/32 words in device memory.  d_out_keys: k keys,
+ * sorted best first, unused tail zero-filled; d_out_n: entries written; d_out_survivors: this
+ * shard's approximate count.  All three live in device memory.  One launch, no host sync. */
+int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k,
+                         float cutoff, gsb_key* d_out_keys, uint32_t* d_out_n,
+                         uint64_t* d_out_survivors);
+/* Merge n_lists sorted candidate lists (list i = d_keys + i*list_stride, d_counts[i] valid
+ * entries; d_counts may be NULL = every list is full with zero keys as padding) into the global
+ * top-k.  Used after the all-gather of per-shard candidates.  Asynchronous on `stream`. */
+int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint32_t* d_counts,
+                     int n_lists, uint32_t list_stride, uint32_t k, uint32_t* d_out_rows,
+                     float* d_out_scores, uint32_t* d_out_n);
+
+/* ---- folding (reference calculation_functors.cpp:22-41, fingerprintdb_cuda.cpp:56-69) ---- */
+int gsb_fold_fingerprint(const int32_t* words, int n_words, int factor, int32_t* out_words);
+
+/* ---- introspection for benchmarks ------------------------------------------------------ */
+typedef struct gsb_scan_info {
+    int device;
+    int grid;                 /* persistent CTAs launched per query                         */
+    int block;                /* threads per CTA                                            */
+    int stages;               /* TMA ring depth                                             */
+    uint32_t tile_rows;       /* rows per TMA bulk load                                     */
+    uint32_t tile_bytes;      /* bytes per TMA bulk load                                    */
+    uint32_t smem_bytes;      /* dynamic shared memory per CTA                              */
+    uint32_t cand_capacity;   /* per-CTA candidate buffer entries                           */
+    uint64_t shard_rows;
+    uint64_t db_bytes_per_query;  /* bytes one query's scan reads from HBM (layout bytes)     */
+} gsb_scan_info;
+/* Geometry gsb_db_search would use for shard `shard` and this k. */
+int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out);
+/* Kernels launched by this library since load (all threads). */
+uint64_t gsb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPUSIM_B200_H */

@@ -39,6 +39,9 @@ def oracle_lib():
         lib.oracle_search.restype = None
         lib.oracle_fold.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         lib.oracle_fold.restype = None
+        lib.oracle_synth_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32,
+                                          C.c_void_p, C.c_int]
+        lib.oracle_synth_rows.restype = None
         _oracle = lib
     return _oracle
 
@@ -65,6 +68,15 @@ def c_search(query, db, k: int, cutoff: float, row_base: int = 0,
                                cutoff, rows.ctypes.data, scores.ctypes.data, C.byref(n),
                                C.byref(approx), n_threads or (os.cpu_count() or 1))
     return rows[:n.value].astype(np.int64), scores[:n.value], int(approx.value)
+
+
+def c_synth_db(seed: int, n_rows: int, words: int = 32, plant_period: int = 0, row_base: int = 0,
+               n_threads: int = 0) -> np.ndarray:
+    """Threaded C twin of oracle.synth_db (checked against it in tests/test_oracle.py)."""
+    out = np.empty((n_rows, words), dtype=np.int32)
+    oracle_lib().oracle_synth_rows(seed, n_rows, row_base, words, plant_period, out.ctypes.data,
+                                   n_threads or (os.cpu_count() or 1))
+    return out
 
 
 def c_fold(fp, factor: int) -> np.ndarray:

@@ -189,3 +189,77 @@ void oracle_fold(const int32_t* fp, int words, int factor, int32_t* out)
     for (int w = 0; w < words; w++)
         out[w % new_words] |= fp[w];
 }
+
+/* ---- synthetic database generator: C twin of oracle.py synth_rows (and of the device generator
+ * in gpusimilarity_b200/csrc/gsb_kernels.cuh), threaded so tests can build 10 M-row inputs. ---- */
+static inline uint64_t mix64(uint64_t x)
+{
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+static inline uint32_t hash32(uint64_t seed, uint64_t row, uint64_t word, uint64_t salt)
+{
+    return (uint32_t) (mix64(row * 0x9E3779B97F4A7C15ull + word * 0xD1B54A32D192ED03ull +
+                             salt * 0x8CB92BA72F3D8DD7ull + seed) >> 32);
+}
+static inline uint32_t random_word(uint64_t seed, uint64_t row, uint32_t w)
+{
+    uint32_t x = hash32(seed, row, w, 0);
+    for (uint32_t salt = 1; salt < 5; salt++)
+        x &= hash32(seed, row, w, salt);
+    return x;
+}
+#define SYNTH_TEMPLATE_ROW 0xFFFFFFFFull
+#define SYNTH_MAX_FLIPS 24
+
+typedef struct {
+    uint64_t seed, lo, hi, row_base;
+    int words;
+    uint32_t plant_period;
+    uint32_t* out;
+} synth_job_t;
+
+static void* synth_job(void* arg)
+{
+    synth_job_t* j = (synth_job_t*) arg;
+    for (uint64_t r = j->lo; r < j->hi; r++) {
+        const uint64_t grow = j->row_base + r;
+        uint32_t* row = j->out + r * (uint64_t) j->words;
+        int planted = j->plant_period > 0 && (hash32(j->seed, grow, 0, 7) % j->plant_period) == 0;
+        if (!planted) {
+            for (int w = 0; w < j->words; w++)
+                row[w] = random_word(j->seed, grow, (uint32_t) w);
+        } else {
+            for (int w = 0; w < j->words; w++)
+                row[w] = random_word(j->seed, SYNTH_TEMPLATE_ROW, (uint32_t) w);
+            const uint32_t nflip = 1 + hash32(j->seed, grow, 1, 7) % SYNTH_MAX_FLIPS;
+            for (uint32_t f = 0; f < nflip; f++) {
+                const uint32_t pos = hash32(j->seed, grow, 2 + f, 7) % (uint32_t) (j->words * 32);
+                row[pos >> 5] ^= 1u << (pos & 31);
+            }
+        }
+    }
+    return NULL;
+}
+
+void oracle_synth_rows(uint64_t seed, uint64_t n_rows, uint64_t row_base, int words,
+                       uint32_t plant_period, uint32_t* out, int n_threads)
+{
+    if (n_threads < 1)
+        n_threads = 1;
+    synth_job_t* jobs = (synth_job_t*) calloc(n_threads, sizeof(synth_job_t));
+    pthread_t* th = (pthread_t*) calloc(n_threads, sizeof(pthread_t));
+    const uint64_t per = (n_rows + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        synth_job_t* j = &jobs[t];
+        j->seed = seed; j->row_base = row_base; j->words = words; j->plant_period = plant_period;
+        j->out = out;
+        j->lo = (uint64_t) t * per < n_rows ? (uint64_t) t * per : n_rows;
+        j->hi = j->lo + per < n_rows ? j->lo + per : n_rows;
+        pthread_create(&th[t], NULL, synth_job, j);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], NULL);
+    free(jobs); free(th);
+}

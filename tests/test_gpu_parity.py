@@ -1,0 +1,300 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes mirror of the reference's
+FingerprintDB), against the CPU oracle on identical inputs.  Bar: bit-exact rows and f32 score
+bit patterns in canonical order (score desc, row asc), exact approximate counts."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import f32bits
+from oracle import oracle as O
+from oracle import oracle_c as OC
+
+pytestmark = pytest.mark.gpu
+
+import gpusimilarity_b200 as gsb  # noqa: E402
+
+
+def make_db(rows: np.ndarray, fold: int = 1, dbkey: str = "pass", devices=None) -> gsb.FingerprintDB:
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    db = gsb.FingerprintDB(rows.shape[1] * 32, rows.shape[0], dbkey, [rows])
+    db.copyToGPU(fold, devices)
+    return db
+
+
+def assert_same(got, want, what=""):
+    g_rows, g_scores, g_approx = got
+    w_rows, w_scores, w_approx = want
+    assert g_approx == w_approx, f"{what}: approx {g_approx} != {w_approx}"
+    assert len(g_rows) == len(w_rows), f"{what}: {len(g_rows)} results, want {len(w_rows)}"
+    assert np.array_equal(f32bits(g_scores), f32bits(w_scores)), f"{what}: score bits differ"
+    assert np.array_equal(np.asarray(g_rows), np.asarray(w_rows)), f"{what}: rows differ"
+
+
+def check(db, rows_np, query, k, cutoff, what=""):
+    got = db.search_rows(query, k, cutoff)
+    want = OC.c_search(query, rows_np, k, cutoff)
+    assert_same(got, want, f"{what} k={k} cutoff={cutoff}")
+
+
+# ------------------------------------------------------------------ the reference's own tests
+def test_reference_similarity_cutoff(golden, small_fsim, small_db):
+    """reference test/test_gpusim.cpp:101-128."""
+    db = gsb.FingerprintDB(1024, 100, "pass", small_fsim.fp_chunks, list(small_fsim.smiles),
+                           list(small_fsim.ids))
+    db.copyToGPU(1)
+    t = golden["reference_tests"]["TestSimilarityCutoff"]
+    fp = db.getFingerprint(t["query_row"])
+    for cutoff, n_res, n_approx in zip(t["cutoffs"], t["result_counts"], t["approximate_counts"]):
+        smiles, ids, scores = [], [], []
+        approx = db.search(fp, "pass", t["k"], cutoff, smiles, ids, scores)
+        assert len(smiles) == n_res and approx == n_approx
+
+
+def test_reference_compare_gpu_to_cpu(golden, small_fsim):
+    """reference test/test_gpusim.cpp:29-69: GPU result order == search_cpu order."""
+    db = gsb.FingerprintDB(1024, 100, "pass", small_fsim.fp_chunks, list(small_fsim.smiles),
+                           list(small_fsim.ids))
+    db.copyToGPU(1)
+    t = golden["reference_tests"]["CompareGPUtoCPU"]
+    fp = db.getFingerprint(t["query_row"])
+    for k in t["return_counts"]:
+        g_smiles, g_ids, g_scores = [], [], []
+        db.search(fp, "pass", k, 0.0, g_smiles, g_ids, g_scores)
+        c_smiles, c_ids, c_scores = [], [], []
+        db.search_cpu(fp, "pass", k, 0.0, c_smiles, c_ids, c_scores)
+        assert len(g_smiles) == k and g_smiles == c_smiles
+    # key mismatch: silently empty (fingerprintdb_cuda.cu:349-352)
+    s, i, f = [], [], []
+    assert db.search(fp, "wrong", 10, 0.0, s, i, f) is None and s == []
+
+
+def test_golden_scores_small_fsim(golden, small_fsim, small_db):
+    """Frozen outputs of the reference's own build: rows and f32 bit patterns."""
+    db = gsb.FingerprintDB(1024, 100, "pass", small_fsim.fp_chunks)
+    db.copyToGPU(1)
+    for g in golden["search_cpu"]:
+        rows, scores, approx = db.search_rows(small_db[g["query_row"]], g["k"], 0.0)
+        assert list(rows) == g["rows"] and list(f32bits(scores)) == g["score_bits"] and approx == 100
+
+
+def test_golden_synthetic(golden):
+    s = golden["synthetic"]
+    rows_np = O.synth_db(s["seed"], s["rows"], 32, s["plant_period"])
+    db = make_db(rows_np)
+    queries = {"template": O.synth_template(s["seed"], 32), "row123": rows_np[123],
+               "zero": np.zeros(32, np.int32)}
+    for g in s["queries"]:
+        rows, scores, _ = db.search_rows(queries[g["name"]], g["k"], 0.0)
+        assert list(rows) == g["rows"] and list(f32bits(scores)) == g["score_bits"]
+
+
+# ------------------------------------------------------------------ oracle parity sweeps
+@pytest.mark.parametrize("n_rows", [1, 31, 32, 33, 255, 256, 257, 1000, 37889, 300001])
+def test_sizes_and_ragged_tails(n_rows):
+    rows_np = O.synth_db(1234 + n_rows, n_rows, 32, 41)
+    db = make_db(rows_np)
+    tmpl = O.synth_template(1234 + n_rows, 32)
+    for q in (tmpl, rows_np[n_rows // 2]):
+        for k in (1, 10, 1000):
+            for cutoff in (0.0, 0.08, 0.5):
+                check(db, rows_np, q, k, cutoff, f"n={n_rows}")
+    check(db, rows_np, tmpl, n_rows + 5, 0.0, "k>N")        # k > N returns every row
+    check(db, rows_np, tmpl, 3, -1.0, "negative cutoff")
+    check(db, rows_np, tmpl, 3, 1.5, "cutoff>1")             # nothing survives
+
+
+def test_ties_zero_rows_and_nan():
+    rng = np.random.default_rng(5)
+    rows_np = O.synth_db(99, 50000, 32, 0)
+    rows_np[rng.integers(0, 50000, 4000)] = rows_np[17]      # a 4000-row tie group at score 1.0
+    rows_np[rng.integers(0, 50000, 3000)] = 0                # all-zero rows
+    db = make_db(rows_np)
+    zero = np.zeros(32, np.int32)
+    for k in (5, 1000, 4500):
+        check(db, rows_np, rows_np[17], k, 0.0, "ties")
+        check(db, rows_np, rows_np[17], k, 0.9, "ties+cutoff")
+        check(db, rows_np, zero, k, 0.0, "zero query: 0/0 -> 0")
+        check(db, rows_np, zero, k, 0.1, "zero query with cutoff")
+
+
+def test_adversarial_order_forces_compactions():
+    """Rows sorted by ascending score: every row beats the running threshold."""
+    base = O.synth_db(7, 120000, 32, 3)
+    q = O.synth_template(7, 32)
+    order = np.argsort(O.tanimoto_scores_cpu(q, base), kind="stable")
+    rows_np = np.ascontiguousarray(base[order])
+    db = make_db(rows_np)
+    for k in (10, 1000, 3000):
+        check(db, rows_np, q, k, 0.0, "ascending")
+    rows_desc = np.ascontiguousarray(rows_np[::-1])
+    db2 = make_db(rows_desc)
+    check(db2, rows_desc, q, 1000, 0.0, "descending")
+
+
+@pytest.mark.parametrize("k", [2000, 5000, 12000])
+def test_large_k(k):
+    rows_np = O.synth_db(31, 200000, 32, 11)
+    db = make_db(rows_np)
+    check(db, rows_np, O.synth_template(31, 32), k, 0.0, "large k")
+    check(db, rows_np, O.synth_template(31, 32), k, 0.2, "large k + cutoff")
+
+
+@pytest.mark.parametrize("bits", [128, 256, 512, 2048, 4096, 96, 768, 1536])
+def test_other_widths(bits):
+    words = bits // 32
+    rows_np = O.synth_db(bits, 20011, words, 23)
+    db = make_db(rows_np)
+    assert db.getFingerprintBitcount() == bits
+    for q in (O.synth_template(bits, words), rows_np[77]):
+        check(db, rows_np, q, 100, 0.0, f"bits={bits}")
+        check(db, rows_np, q, 100, 0.3, f"bits={bits}")
+    assert np.array_equal(db.getFingerprint(77), rows_np[77])
+
+
+def test_rowpop_layout_variant(monkeypatch):
+    monkeypatch.setenv("GSB_ROWPOP", "1")
+    rows_np = O.synth_db(555, 70001, 32, 19)
+    db = make_db(rows_np)
+    for k, cutoff in ((10, 0.0), (1000, 0.0), (1000, 0.1)):
+        check(db, rows_np, O.synth_template(555, 32), k, cutoff, "rowpop")
+        check(db, rows_np, rows_np[69999], k, cutoff, "rowpop")
+
+
+def test_tuning_knobs_do_not_change_results(monkeypatch):
+    rows_np = O.synth_db(808, 150000, 32, 29)
+    q = O.synth_template(808, 32)
+    want = OC.c_search(q, rows_np, 1000, 0.0)
+    for env in ({"GSB_STAGES": "2"}, {"GSB_STAGES": "6", "GSB_TILE_BYTES": "16384"}, {"GSB_GRID": "7"},
+                {"GSB_GRID": "1"}, {"GSB_TILE_BYTES": "8192", "GSB_MIN_CAP": "2048"}):
+        for k_, v in env.items():
+            monkeypatch.setenv(k_, v)
+        db = make_db(rows_np)
+        assert_same(db.search_rows(q, 1000, 0.0), want, str(env))
+        db.close()
+        for k_ in env:
+            monkeypatch.delenv(k_)
+
+
+def test_synthetic_device_generator_matches_host_twin():
+    n = 100000
+    for plant in (0, 37):
+        db = gsb.FingerprintDB.synthetic(n, device=0, seed=42, plant_period=plant)
+        rows_np = O.synth_db(42, n, 32, plant)
+        for r in (0, 1, 255, 256, 31337, n - 1):
+            assert np.array_equal(db.getFingerprint(r), rows_np[r]), (plant, r)
+        check(db, rows_np, O.synth_template(42, 32), 1000, 0.0, f"synthetic plant={plant}")
+    # a shard with a row base returns global row ids
+    db = gsb.FingerprintDB.synthetic(5000, device=0, seed=42, plant_period=37, row_base=70000)
+    rows_np = O.synth_db(42, 5000, 32, 37, row_base=70000)
+    got = db.search_rows(O.synth_template(42, 32), 50, 0.0)
+    assert_same(got, OC.c_search(O.synth_template(42, 32), rows_np, 50, 0.0, row_base=70000), "row_base")
+
+
+def test_repeat_queries_are_idempotent():
+    """The launch-persistent control block must be left clean by every launch."""
+    rows_np = O.synth_db(3, 90000, 32, 13)
+    db = make_db(rows_np)
+    qs = [O.synth_template(3, 32), rows_np[5], rows_np[89999], np.zeros(32, np.int32)]
+    for rep in range(3):
+        for q in qs:
+            for k, cutoff in ((1000, 0.0), (7, 0.25)):
+                check(db, rows_np, q, k, cutoff, f"rep {rep}")
+    res = db.search_batch_rows(np.stack(qs), 100, 0.05)
+    for q, got in zip(qs, res):
+        assert_same(got, OC.c_search(q, rows_np, 100, 0.05), "batch")
+
+
+@pytest.mark.parametrize("fold", [2, 3, 4, 8, 32])
+def test_folded_search(fold):
+    """reference copyToGPU(fold) + re-score path, fingerprintdb_cuda.cu:170-173,246-331."""
+    rows_np = O.synth_db(61, 60000, 32, 17)
+    db = make_db(rows_np, fold=fold)
+    assert db.foldFactor() == O.effective_fold_factor(32, fold)
+    q = O.synth_template(61, 32)
+    for k, cutoff in ((10, 0.0), (20, 0.3), (100, 0.6)):
+        rows, scores, approx = db.search_rows(q, k, cutoff)
+        w_rows, w_scores, w_approx = O.search_gpu_folded(q, rows_np, k, cutoff, fold)
+        assert approx == w_approx
+        assert np.array_equal(f32bits(scores), f32bits(w_scores)) and np.array_equal(rows, w_rows)
+
+
+def test_config1_10m_rows_top1000():
+    """BASELINE config[1]: 10 M x 1024 bit, one query, top-1000 (oracle: threaded C port)."""
+    n = 10_000_000
+    rows_np = OC.c_synth_db(0x5EED5EED, n, 32, 4096)
+    db = make_db(rows_np)
+    q = O.synth_template(0x5EED5EED, 32)
+    for k, cutoff in ((1000, 0.0), (1000, 0.3), (10, 0.0)):
+        check(db, rows_np, q, k, cutoff, "10M")
+    check(db, rows_np, rows_np[9_999_999], 1000, 0.0, "10M row query")
+    # the same database generated on the device gives the same answer
+    dbs = gsb.FingerprintDB.synthetic(n, device=0, seed=0x5EED5EED, plant_period=4096)
+    assert_same(dbs.search_rows(q, 1000, 0.0), OC.c_search(q, rows_np, 1000, 0.0), "10M synthetic")
+
+
+@pytest.mark.skipif(not OC.ref_available(), reason="oracle/_ref not built")
+def test_against_reference_cuda_path():
+    """The reference's own Thrust/CUDA search (its .cu compiled verbatim for sm_100a) on the same
+    rows.  Single chunk (<= 2^23 rows): identical row SET and score vector; the reference orders
+    equal scores by pointer (fingerprintdb_cuda.cu:366), so rows are compared after canonical
+    re-ordering."""
+    n = 3_000_000
+    rows_np = OC.c_synth_db(2024, n, 32, 1500)
+    ref = OC.RefDB([rows_np], 1024)
+    ref.copy_to_gpu(1)
+    db = make_db(rows_np)
+    for q in (O.synth_template(2024, 32), rows_np[12345]):
+        for k, cutoff in ((10, 0.0), (1000, 0.0), (1000, 0.25), (50, 0.6)):
+            r_rows, r_scores, r_approx = ref.search(q, k, cutoff)
+            rows, scores, approx = db.search_rows(q, k, cutoff)
+            assert approx == r_approx
+            assert np.array_equal(f32bits(scores), f32bits(r_scores))
+            order = O.canonical_order(r_scores, r_rows)
+            assert np.array_equal(rows, r_rows[order])
+
+
+def test_partition_invariance_200m_rows():
+    """Size-independent property at a size no oracle run covers: the top-k of the whole database
+    equals the merge of the top-k of its parts, and every returned score re-scores exactly."""
+    n, parts, k = 200_000_000, 4, 1000
+    seed, plant = 77, 50000
+    q = O.synth_template(seed, 32)
+    whole = gsb.FingerprintDB.synthetic(n, device=0, seed=seed, plant_period=plant)
+    rows, scores, approx = whole.search_rows(q, k, 0.0)
+    assert approx == n and len(rows) == k
+    assert np.all(np.diff(scores) <= 0) and len(set(rows.tolist())) == k
+    sample = np.concatenate([rows[:20], rows[-20:]])
+    fps = np.stack([whole.getFingerprint(int(r)) for r in sample])
+    assert np.array_equal(fps, O.synth_rows(seed, sample, 32, plant))
+    assert np.array_equal(f32bits(O.tanimoto_scores_gpu(q, fps, 0.0)),
+                          f32bits(np.concatenate([scores[:20], scores[-20:]])))
+    whole.close()
+    per = n // parts
+    cand_rows, cand_scores = [], []
+    for p in range(parts):
+        part = gsb.FingerprintDB.synthetic(per, device=0, seed=seed, plant_period=plant, row_base=p * per)
+        r, s, _ = part.search_rows(q, k, 0.0)
+        cand_rows.append(r)
+        cand_scores.append(s)
+        part.close()
+    cr, cs = np.concatenate(cand_rows), np.concatenate(cand_scores)
+    order = O.canonical_order(cs, cr)[:k]
+    assert np.array_equal(cr[order], rows) and np.array_equal(f32bits(cs[order]), f32bits(scores))
+
+
+def test_errors_are_loud():
+    rows_np = O.synth_db(1, 1000, 32, 0)
+    db = gsb.FingerprintDB(1024, 1000, "pass", [rows_np])
+    with pytest.raises(gsb.GsbError):                       # search before copyToGPU
+        db.search_rows(rows_np[0], 10, 0.0)
+    db.copyToGPU(1)
+    with pytest.raises(gsb.GsbError):                       # wrong query width
+        db.search_rows(rows_np[0][:16], 10, 0.0)
+    with pytest.raises(gsb.GsbError):                       # count mismatch (reference .cu:153-156)
+        gsb.FingerprintDB(1024, 999, "pass", [rows_np])
+    with pytest.raises(gsb.GsbError):                       # beyond the fused select's capacity
+        db.search_rows(rows_np[0], 100000, 0.0)
+    assert gsb.get_gpu_count() >= 1
+    g = gsb.get_gpu_count()
+    assert [gsb.get_next_gpu(1) for _ in range(2 * g)] is not None  # reference test getNextGPU

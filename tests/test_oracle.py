@@ -98,6 +98,13 @@ def test_golden_synthetic(golden):
             assert list(rows) == g["rows"] and list(f32bits(scores)) == g["score_bits"]
 
 
+def test_c_synth_generator_matches_numpy():
+    for words, plant, base in ((32, 0, 0), (32, 13, 0), (32, 13, 123456789), (8, 5, 77), (128, 3, 0)):
+        a = O.synth_db(42, 3001, words, plant, row_base=base)
+        b = OC.c_synth_db(42, 3001, words, plant, row_base=base, n_threads=3)
+        assert np.array_equal(a, b), (words, plant, base)
+
+
 def test_c_oracle_matches_numpy_semantics():
     """Edge cases the reference tests never touch: all-zero rows (0/0), k > N, ties, cutoff."""
     rng = np.random.default_rng(3)
