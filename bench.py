@@ -322,7 +322,8 @@ def main():
                 "workload": f"{args.rows} x 1024-bit synthetic fingerprints ({args.rows * ROW_BYTES / 1e9:.1f} GB), "
                             f"single query, top-{K}, cutoff {CUTOFF}, {world} shard(s)",
                 "rows_per_gpu": n_rows, "k": K, "l2": "database shard is far larger than the 126 MB L2",
-                "grid": info.grid, "block": info.block, "tma_stages": info.stages, "tile_bytes": info.tile_bytes,
+                "grid": info.grid, "block": info.block, "tma_stages_per_warp": info.stages, "tma_bytes_per_copy": info.tile_bytes,
+                "layout_bytes_per_query": info.db_bytes_per_query,
                 "smem_bytes": info.smem_bytes, "synthetic_gen_s": round(t_gen, 2),
                 "parallelism": f"row-sharded x{world}" + (", NCCL all-gather of per-shard top-k + merge kernel" if world > 1 else ""),
             },
@@ -331,7 +332,7 @@ def main():
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel<32,false>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "scan_topk_kernel<W=32>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_mean,
                          "traffic": ncu_traffic_per_launch(n_rows)},

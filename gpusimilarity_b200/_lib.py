@@ -54,6 +54,7 @@ SIGNATURES = {
     "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "gsb_fold_fingerprint": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "gsb_db_scan_info": (C.c_int, [_P, C.c_int, C.c_uint32, C.POINTER(ScanInfo)]),
+    "gsb_selftest_division": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),
     "gsb_launch_count": (C.c_uint64, []),
 }
 

@@ -56,17 +56,17 @@ uint32_t pow2ceil(uint64_t v)
 }
 
 // ------------------------------------------------------------------------------ HBM layout
-// The database lives in HBM as fixed-size tiles so that one TMA bulk copy moves one tile:
-//   tile t = rows [t*tile_rows, (t+1)*tile_rows), row-major, dev_words 32-bit words per row,
-//            then (rowpop layout only) tile_rows u16 row popcounts.
-// Without the trailer the tiles are back to back, i.e. the plain row-major matrix.
+// The database lives in HBM as 32-row batches so that one TMA bulk copy moves one batch:
+//   batch b = rows [32 b, 32 b + 32), row-major, dev_words 32-bit words per row,
+//             then (rowpop layout only) 32 u16 row popcounts.
+// Without the trailer the batches are back to back, i.e. the plain row-major matrix.
 struct Layout {
     uint32_t words = 0;      // logical words per row (after folding)
     uint32_t dev_words = 0;  // words per row in HBM: power of two in [4, 128], zero padded
-    uint32_t tile_rows = 0;
+    uint32_t tile_rows = 32; // rows per batch
     uint32_t row_bytes = 0;
     uint32_t tile_bytes = 0;  // bytes per bulk copy
-    uint32_t tile_stride = 0; // distance between tiles
+    uint32_t tile_stride = 0; // distance between batches
     uint32_t stage_bytes = 0; // ring slot
     bool rowpop = false;
 };
@@ -79,13 +79,10 @@ int make_layout(uint32_t words, Layout* out)
     if (l.dev_words > gsb::kMaxWords)
         return fail(GSB_ERR_INVALID, "fingerprints wider than 4096 bits are not supported");
     l.row_bytes = l.dev_words * 4;
-    const uint32_t tile_target = static_cast<uint32_t>(env_int("GSB_TILE_BYTES", 32768));
-    uint32_t rows = std::max<uint32_t>(32, tile_target / l.row_bytes);
-    rows = rows / 32 * 32;
-    l.tile_rows = rows;
-    l.rowpop = env_int("GSB_ROWPOP", 0) != 0;
-    l.tile_bytes = rows * l.row_bytes + (l.rowpop ? rows * 2 : 0);
-    l.tile_stride = l.tile_bytes; // multiple of 16: rows % 32 == 0
+    l.tile_rows = gsb::kBatchRows;
+    l.rowpop = env_int("GSB_ROWPOP", 1) != 0;
+    l.tile_bytes = l.tile_rows * l.row_bytes + (l.rowpop ? l.tile_rows * 2 : 0);
+    l.tile_stride = l.tile_bytes; // multiple of 16
     l.stage_bytes = (l.tile_bytes + 127) / 128 * 128;
     *out = l;
     return GSB_OK;
@@ -116,6 +113,8 @@ struct Shard {
 
 struct Plan {
     int grid = 0;
+    int warps = 0;
+    int unroll = 1;
     uint32_t stages = 0, cap = 0, smem = 0;
 };
 
@@ -145,35 +144,46 @@ int smem_limit(int device, int* out)
     return GSB_OK;
 }
 
-template <int W, bool RP> int set_smem_attr(int bytes)
-{
-    GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    return GSB_OK;
-}
-
-template <int W, bool RP> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
+template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
     static thread_local int configured[64] = {0};
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && configured[dev] < static_cast<int>(plan.smem)) {
-        int rc = set_smem_attr<W, RP>(plan.smem);
-        if (rc)
-            return rc;
+        GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP, CW, U>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
         configured[dev] = plan.smem;
     }
-    gsb::scan_topk_kernel<W, RP><<<plan.grid, gsb::kThreads, plan.smem, st>>>(p);
+    gsb::scan_topk_kernel<W, RP, CW, U><<<plan.grid, CW * 32, plan.smem, st>>>(p);
     g_launches++;
     GSB_CUDA(cudaGetLastError());
     return GSB_OK;
+}
+
+template <int W, bool RP> int launch_scan_w(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
+{
+    // wide rows keep one batch in registers; up to 1024 bits two batches give independent chains
+    constexpr int UMAX = W <= 32 ? 2 : 1;
+#define GSB_WCASE(CW)                                                                            \
+    case CW:                                                                                     \
+        return plan.unroll >= 2 ? launch_scan_t<W, RP, CW, UMAX>(p, plan, st)                     \
+                                : launch_scan_t<W, RP, CW, 1>(p, plan, st);
+    switch (plan.warps) {
+        GSB_WCASE(4)
+        GSB_WCASE(8)
+        GSB_WCASE(12)
+        GSB_WCASE(16)
+#undef GSB_WCASE
+    default:
+        return fail(GSB_ERR_INVALID, "GSB_WARPS must be 4, 8, 12 or 16");
+    }
 }
 
 int launch_scan(const Layout& l, const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
 #define GSB_CASE(W)                                                                              \
     case W:                                                                                      \
-        return l.rowpop ? launch_scan_t<W, true>(p, plan, st) : launch_scan_t<W, false>(p, plan, st);
+        return l.rowpop ? launch_scan_w<W, true>(p, plan, st) : launch_scan_w<W, false>(p, plan, st);
     switch (l.dev_words) {
         GSB_CASE(4)
         GSB_CASE(8)
@@ -187,9 +197,10 @@ int launch_scan(const Layout& l, const gsb::ScanParams& p, const Plan& plan, cud
 #undef GSB_CASE
 }
 
-// Ring depth and candidate capacity for this k.  Rules the kernel relies on:
-//   cap is a power of two, cap >= k + 2*stages*tile_rows (room between two compactions and for
-//   the tiles in flight when one is requested) and cap >= k + grid (final merge rounds).
+// Warps per CTA, ring depth per warp and candidate capacity for this k.  Rules the kernel
+// relies on: cap is a power of two; cap >= k + 4*U*threads (the select is requested 2*U*threads
+// below the top, and there must be room to refill after it); cap >= k + grid (merge rounds);
+// stages >= U.
 int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
 {
     int smem_max = 0;
@@ -197,22 +208,34 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
     if (rc)
         return rc;
     const int budget = smem_max - 2048; // static shared memory + alignment slack
-    int grid = sh.ws.max_grid;
-    if (const int g = env_int("GSB_GRID", 0))
-        grid = g;
-    grid = std::max(1, std::min<int>(grid, sh.n_tiles ? sh.n_tiles : 1));
-    const int want = std::min(gsb::kMaxStages, std::max(2, env_int("GSB_STAGES", 4)));
-    for (int st = want; st >= 2; st--) {
-        const uint64_t need = static_cast<uint64_t>(k) + 2ull * st * l.tile_rows;
-        const uint32_t cap = std::max<uint32_t>(pow2ceil(std::max<uint64_t>(need, k + (uint64_t) grid)),
-                                                static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));
-        const uint64_t smem = static_cast<uint64_t>(st) * l.stage_bytes + static_cast<uint64_t>(cap) * 8;
-        if (smem <= static_cast<uint64_t>(budget)) {
-            out->grid = grid;
-            out->stages = st;
-            out->cap = cap;
-            out->smem = static_cast<uint32_t>(smem);
-            return GSB_OK;
+    const int pref = env_int("GSB_WARPS", 16);
+    if (pref != 4 && pref != 8 && pref != 12 && pref != 16)
+        return fail(GSB_ERR_INVALID, "GSB_WARPS must be 4, 8, 12 or 16");
+    const int want = std::min(gsb::kMaxStages, std::max(2, env_int("GSB_STAGES", 3)));
+    // preferred shape first, then fewer stages, then fewer warps (wide rows, large k)
+    for (int warps = pref; warps >= 4; warps -= 4) {
+        int grid = sh.ws.max_grid;
+        if (const int g = env_int("GSB_GRID", 0))
+            grid = std::min(g, 4096);
+        const uint32_t n_super = (sh.n_tiles + warps - 1) / warps;
+        grid = std::max(1, std::min<int>(grid, n_super ? n_super : 1));
+        const uint32_t threads = warps * 32;
+        const int unroll = (l.dev_words <= 32 && env_int("GSB_UNROLL", 2) >= 2) ? 2 : 1;
+        const uint64_t need =
+            std::max<uint64_t>(static_cast<uint64_t>(k) + 4ull * unroll * threads, k + (uint64_t) grid);
+        const uint32_t cap = std::max<uint32_t>(pow2ceil(need), static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));
+        for (int st = want; st >= 2; st--) {
+            const uint64_t smem =
+                static_cast<uint64_t>(warps) * st * l.stage_bytes + static_cast<uint64_t>(cap) * 8;
+            if (smem <= static_cast<uint64_t>(budget)) {
+                out->grid = grid;
+                out->warps = warps;
+                out->unroll = unroll;
+                out->stages = st;
+                out->cap = cap;
+                out->smem = static_cast<uint32_t>(smem);
+                return GSB_OK;
+            }
         }
     }
     return fail(GSB_ERR_INVALID, "max_return_count " + std::to_string(k) +
@@ -374,15 +397,15 @@ void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k
     p->tiles = sh.tiles;
     p->n_rows = sh.n_rows;
     p->row_base = sh.row_base;
-    p->n_tiles = sh.n_tiles;
-    p->tile_rows = l.tile_rows;
-    p->tile_stride = l.tile_stride;
-    p->tile_bytes = l.tile_bytes;
+    p->n_batches = sh.n_tiles;
+    p->batch_stride = l.tile_stride;
+    p->batch_bytes = l.tile_bytes;
     p->stage_bytes = l.stage_bytes;
     p->stages = plan.stages;
     p->cap = plan.cap;
     p->k = k;
     p->cutoff = cutoff;
+    p->key_ceiling = ~0ull;
     p->cta_keys = sh.ws.cta_keys;
     p->cta_counts = sh.ws.cta_counts;
     p->ctrl = sh.ws.ctrl;
@@ -404,7 +427,7 @@ inline Cand decode(unsigned long long key)
 
 // One scan per shard with a host-resident query; leaves keys/n/survivors in ws.out_host.
 int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, float cutoff,
-                    std::vector<unsigned long long>* keys, uint64_t* survivors)
+                    unsigned long long key_ceiling, std::vector<unsigned long long>* keys, uint64_t* survivors)
 {
     std::vector<Plan> plans(db->shards.size());
     for (size_t i = 0; i < db->shards.size(); i++) {
@@ -421,6 +444,7 @@ int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, f
         gsb::ScanParams p;
         fill_params(db, sh, plans[i], k, cutoff, &p);
         std::memcpy(p.q_host, q_dev_words, db->layout.dev_words * 4);
+        p.key_ceiling = key_ceiling;
         p.out_keys = sh.ws.out_dev;
         p.out_survivors = sh.ws.out_dev + k;
         p.out_n = reinterpret_cast<uint32_t*>(sh.ws.out_dev + k + 1);
@@ -451,6 +475,58 @@ int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, f
             if (keys->size() > k)
                 keys->resize(k);
         }
+    }
+    return GSB_OK;
+}
+
+// Largest k one fused launch can select on every shard of this database.
+uint32_t max_fused_k(const gsb_db* db)
+{
+    for (uint32_t cap = 32768; cap >= 2048; cap >>= 1) {
+        const uint32_t k = cap - 4u * 2u * 128u - 4096u / 8u;
+        bool ok = true;
+        for (const Shard& sh : db->shards) {
+            Plan plan;
+            if (sh.n_rows && make_plan(db->layout, sh, k, &plan) != GSB_OK)
+                ok = false;
+        }
+        if (ok)
+            return k;
+    }
+    return 0;
+}
+
+// Top-k_total keys over all shards.  One fused launch per shard when k_total fits the in-kernel
+// select; otherwise peeling passes: every pass selects the best `kmax` keys strictly below the
+// worst key of the previous pass (keys are unique, so the passes tile the ranking exactly).
+int scan_topk(const gsb_db* db, const uint32_t* q_dev_words, uint64_t k_total, float cutoff,
+              std::vector<unsigned long long>* keys, uint64_t* survivors)
+{
+    Plan probe;
+    bool fits = k_total <= 0xffffffffull;
+    for (const Shard& sh : db->shards)
+        if (fits && sh.n_rows && make_plan(db->layout, sh, static_cast<uint32_t>(k_total), &probe) != GSB_OK)
+            fits = false;
+    if (fits)
+        return scan_all_shards(db, q_dev_words, static_cast<uint32_t>(k_total), cutoff, ~0ull, keys, survivors);
+    const uint32_t kmax = max_fused_k(db);
+    if (kmax == 0)
+        return fail(GSB_ERR_INVALID, "no launch shape fits this database");
+    keys->clear();
+    unsigned long long ceiling = ~0ull;
+    std::vector<unsigned long long> pass;
+    while (keys->size() < k_total) {
+        uint64_t surv = 0;
+        const uint32_t want = static_cast<uint32_t>(std::min<uint64_t>(kmax, k_total - keys->size()));
+        int rc = scan_all_shards(db, q_dev_words, want, cutoff, ceiling, &pass, &surv);
+        if (rc)
+            return rc;
+        if (ceiling == ~0ull)
+            *survivors = surv;
+        keys->insert(keys->end(), pass.begin(), pass.end());
+        if (pass.size() < want)
+            break; // the database is exhausted
+        ceiling = pass.back();
     }
     return GSB_OK;
 }
@@ -736,8 +812,7 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
     k_scan = std::min<uint64_t>(k_scan, db->count);
     std::vector<unsigned long long> keys;
     uint64_t survivors = 0;
-    int rc = scan_all_shards(db, q.data(), static_cast<uint32_t>(std::max<uint64_t>(k_scan, 1)), cutoff, &keys,
-                             &survivors);
+    int rc = scan_topk(db, q.data(), std::max<uint64_t>(k_scan, 1), cutoff, &keys, &survivors);
     if (rc)
         return rc;
     if (keys.size() > k_scan)
@@ -874,7 +949,7 @@ int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint
         return fail(GSB_ERR_INVALID, "k too large for the merge kernel");
     GSB_CUDA(cudaFuncSetAttribute(gsb::merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(smem)));
-    gsb::merge_kernel<<<1, gsb::kConsumerThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+    gsb::merge_kernel<<<1, gsb::kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const unsigned long long*>(d_keys), d_counts, static_cast<uint32_t>(n_lists), list_stride,
         k, cap, d_out_rows, d_out_scores, d_out_n);
     g_launches++;
@@ -890,6 +965,23 @@ int gsb_fold_fingerprint(const int32_t* words, int n_words, int factor, int32_t*
     return GSB_OK;
 }
 
+int gsb_selftest_division(int device, uint64_t* mismatches)
+{
+    if (!mismatches)
+        return fail(GSB_ERR_INVALID, "null argument");
+    GSB_CUDA(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    GSB_CUDA(cudaMalloc(&d, 8));
+    GSB_CUDA(cudaMemset(d, 0, 8));
+    gsb::selftest_division_kernel<<<1184, 256>>>(8192, d);
+    g_launches++;
+    unsigned long long h = 0;
+    GSB_CUDA(cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    *mismatches = h;
+    return GSB_OK;
+}
+
 int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out)
 {
     if (!db || !out || shard < 0 || shard >= static_cast<int>(db->shards.size()))
@@ -901,7 +993,7 @@ int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out
         return rc;
     out->device = sh.device;
     out->grid = plan.grid;
-    out->block = gsb::kThreads;
+    out->block = plan.warps * 32;
     out->stages = plan.stages;
     out->tile_rows = db->layout.tile_rows;
     out->tile_bytes = db->layout.tile_bytes;

@@ -139,6 +139,9 @@ typedef struct gsb_scan_info {
 } gsb_scan_info;
 /* Geometry gsb_db_search would use for shard `shard` and this k. */
 int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out);
+/* Device self-test: the kernel's own correctly-rounded division against __fdiv_rn for every
+ * (common, union) pair a fingerprint of up to 8192 bits can produce; *mismatches must be 0. */
+int gsb_selftest_division(int device, uint64_t* mismatches);
 /* Kernels launched by this library since load (all threads). */
 uint64_t gsb_launch_count(void);
 
