@@ -184,6 +184,7 @@ def main():
     import numpy as np
     import torch
     import gpusimilarity_b200 as gsb
+    from gpusimilarity_b200.dist import ShardedSearcher, shard_range
     from oracle import oracle as O   # checker only: verifies the timed results afterwards
 
     if not torch.cuda.is_available() or gsb.get_gpu_count() == 0:
@@ -201,9 +202,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- the database: contiguous, equal shards of the synthetic rows, generated in HBM
-    per = (args.rows + world - 1) // world
-    row_base = min(args.rows, rank * per)
-    n_rows = min(per, args.rows - row_base)
+    row_base, n_rows = shard_range(args.rows, rank, world)
     t_gen = time.perf_counter()
     db = gsb.FingerprintDB.synthetic(n_rows, device=local_rank, seed=SEED, plant_period=PLANT_PERIOD,
                                      row_base=row_base)
@@ -215,37 +214,21 @@ def main():
     q_pinned = torch.from_numpy(query_np.copy()).pin_memory()
     d_query = q_pinned.to(dev)
     stream = torch.cuda.current_stream()
-    # per-rank candidate record: [K keys][survivors][n] as int64
-    rec = torch.zeros(K + 2, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(world * (K + 2), dtype=torch.int64, device=dev)
-    out_rows = torch.zeros(K, dtype=torch.int32, device=dev)
-    out_scores = torch.zeros(K, dtype=torch.float32, device=dev)
-    out_n = torch.zeros(1, dtype=torch.int32, device=dev)
-    h_rows = torch.zeros(K, dtype=torch.int32).pin_memory()
-    h_scores = torch.zeros(K, dtype=torch.float32).pin_memory()
-    keys_ptr = rec.data_ptr()
-    surv_ptr = keys_ptr + 8 * K
-    n_ptr = keys_ptr + 8 * (K + 1)
+    searcher = ShardedSearcher(db, K, local_rank, dist, world)
 
     def device_step(q_ptr):
         """scan (1 launch) [+ all-gather + merge (1 launch) when sharded]; results stay in HBM."""
-        db.search_device(stream.cuda_stream, q_ptr, K, CUTOFF, keys_ptr, n_ptr, surv_ptr)
-        if dist is not None:
-            dist.all_gather_into_tensor(gathered, rec)
-            gsb.merge_device(local_rank, stream.cuda_stream, gathered.data_ptr(), None, world, K + 2, K,
-                             out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
+        if dist is None:
+            searcher.search_local(q_ptr, CUTOFF, stream)
+        else:
+            searcher.search_device(q_ptr, CUTOFF, stream)
 
     def e2e_step():
         """Public host-buffer call: pinned query in, rows + scores back on the host."""
         if dist is None:
             return db.search_rows(query_np, K, CUTOFF)
-        d_query.copy_(q_pinned, non_blocking=True)
-        device_step(d_query.data_ptr())
-        h_rows.copy_(out_rows, non_blocking=True)
-        h_scores.copy_(out_scores, non_blocking=True)
-        torch.cuda.synchronize()
-        n = int(out_n.item())
-        return h_rows[:n].numpy().astype(np.int64) & 0xffffffff, h_scores[:n].numpy(), None
+        rows, scores = searcher.search_host(d_query, q_pinned, CUTOFF, stream)
+        return rows, scores, None
 
     # ---- warm-up
     for _ in range(args.warmup):
@@ -276,7 +259,7 @@ def main():
     for _ in range(args.steps):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
-        db.search_device(stream.cuda_stream, d_query.data_ptr(), K, CUTOFF, keys_ptr, n_ptr, surv_ptr)
+        searcher.search_local(d_query.data_ptr(), CUTOFF, stream)
         b.record(stream)
         b.synchronize()
         kern_ms.append(a.elapsed_time(b))

@@ -162,12 +162,11 @@ template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams
 
 template <int W, bool RP> int launch_scan_w(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
-    // wide rows keep one batch in registers; up to 1024 bits two batches give independent chains
-    constexpr int UMAX = W <= 32 ? 2 : 1;
+    // U (batches per iteration) = 1: with 12-16 warps per SM a second in-register batch only adds
+    // register pressure (measured, profiles/r01_sweep.md); the kernel keeps the template knob.
 #define GSB_WCASE(CW)                                                                            \
     case CW:                                                                                     \
-        return plan.unroll >= 2 ? launch_scan_t<W, RP, CW, UMAX>(p, plan, st)                     \
-                                : launch_scan_t<W, RP, CW, 1>(p, plan, st);
+        return launch_scan_t<W, RP, CW, 1>(p, plan, st);
     switch (plan.warps) {
         GSB_WCASE(4)
         GSB_WCASE(8)
@@ -220,7 +219,7 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
         const uint32_t n_super = (sh.n_tiles + warps - 1) / warps;
         grid = std::max(1, std::min<int>(grid, n_super ? n_super : 1));
         const uint32_t threads = warps * 32;
-        const int unroll = (l.dev_words <= 32 && env_int("GSB_UNROLL", 2) >= 2) ? 2 : 1;
+        const int unroll = 1;
         const uint64_t need =
             std::max<uint64_t>(static_cast<uint64_t>(k) + 4ull * unroll * threads, k + (uint64_t) grid);
         const uint32_t cap = std::max<uint32_t>(pow2ceil(need), static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));

@@ -294,6 +294,40 @@ def test_partition_invariance_200m_rows():
     assert np.array_equal(cr[order], rows) and np.array_equal(f32bits(cs[order]), f32bits(scores))
 
 
+def test_device_entry_points_and_merge_kernel():
+    """The one-process-per-GPU path on one GPU: three shards with row bases, searched through
+    gsb_db_search_device on a torch stream, merged by gsb_merge_device."""
+    import torch
+    from gpusimilarity_b200.dist import ShardedSearcher, shard_range, RECORD_EXTRA
+    n, k, seed, plant = 900_000, 1000, 21, 700
+    whole_np = OC.c_synth_db(seed, n, 32, plant)
+    q_np = O.synth_template(seed, 32)
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(q_np.copy()).to(dev)
+    stream = torch.cuda.current_stream()
+    for cutoff in (0.0, 0.2):
+        recs, approx = [], 0
+        for r in range(3):
+            base, rows = shard_range(n, r, 3)
+            shard = gsb.FingerprintDB.synthetic(rows, device=0, seed=seed, plant_period=plant, row_base=base)
+            s = ShardedSearcher(shard, k, 0)
+            s.search_local(d_q.data_ptr(), cutoff, stream)
+            torch.cuda.synchronize()
+            recs.append(s.rec.clone())
+            approx += s.approx_count()
+            shard.close()
+        gathered = torch.cat(recs)
+        out_rows = torch.zeros(k, dtype=torch.int32, device=dev)
+        out_scores = torch.zeros(k, dtype=torch.float32, device=dev)
+        out_n = torch.zeros(1, dtype=torch.int32, device=dev)
+        gsb.merge_device(0, stream.cuda_stream, gathered.data_ptr(), None, 3, k + RECORD_EXTRA, k,
+                         out_rows.data_ptr(), out_scores.data_ptr(), out_n.data_ptr())
+        torch.cuda.synchronize()
+        cnt = int(out_n.item())
+        got = (out_rows[:cnt].cpu().numpy().astype(np.int64) & 0xffffffff, out_scores[:cnt].cpu().numpy(), approx)
+        assert_same(got, OC.c_search(q_np, whole_np, k, cutoff), f"3 shards cutoff={cutoff}")
+
+
 def test_errors_are_loud():
     rows_np = O.synth_db(1, 1000, 32, 0)
     db = gsb.FingerprintDB(1024, 1000, "pass", [rows_np])

@@ -58,6 +58,35 @@ __global__ void __launch_bounds__(288, 1) read_tma_kernel(const uint8_t* base, u
     if (acc == 0x12345678) *sink = acc;
 }
 
+// Per-warp private rings (the product kernel's access pattern) with no compute.
+__global__ void __launch_bounds__(512, 1) read_tma_warp_kernel(const uint8_t* base, uint32_t n_batches, uint32_t bytes,
+                                                              uint32_t stride, uint32_t stages, uint32_t* sink)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t full[16 * 8];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, cw = blockDim.x >> 5;
+    const uint32_t stage_bytes = (bytes + 127) / 128 * 128;
+    uint8_t* ring = smem + (size_t) warp * stages * stage_bytes;
+    uint64_t* my = full + warp * 8;
+    if (lane == 0) { for (uint32_t s = 0; s < stages; s++) gsb::mbar_init(&my[s], 1); gsb::mbar_fence_init(); }
+    __syncthreads();
+    const uint32_t step = gridDim.x * cw;
+    uint32_t b = blockIdx.x * cw + warp;
+    if (lane == 0)
+        for (uint32_t s = 0; s < stages; s++)
+            if (b + s * step < n_batches) { gsb::mbar_arrive_expect_tx(&my[s], bytes); gsb::tma_bulk_g2s(ring + s * stage_bytes, base + (uint64_t)(b + s * step) * stride, bytes, &my[s]); }
+    uint32_t acc = 0, st = 0, ph = 0;
+    for (; b < n_batches; b += step) {
+        gsb::mbar_wait(&my[st], ph);
+        acc += reinterpret_cast<const uint32_t*>(ring + st * stage_bytes)[lane];
+        __syncwarp();
+        const uint32_t nb = b + stages * step;
+        if (lane == 0 && nb < n_batches) { gsb::mbar_arrive_expect_tx(&my[st], bytes); gsb::tma_bulk_g2s(ring + st * stage_bytes, base + (uint64_t) nb * stride, bytes, &my[st]); }
+        if (++st == stages) { st = 0; ph ^= 1; }
+    }
+    if (acc == 0x12345678) *sink = acc;
+}
+
 template <int MODE> __global__ void alu_kernel(uint32_t* out, int iters)
 {
     uint32_t a[8];
@@ -110,6 +139,24 @@ int main(int argc, char** argv)
                 best = fminf(best, time_ms(e0, e1));
             }
             printf("read_tma  tile=%6u stages=%u      : %8.1f GB/s\n", tile, stages, bytes / best / 1e6);
+        }
+    }
+    CK(cudaFuncSetAttribute(read_tma_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    for (uint32_t bytes : {4096u, 4160u, 8192u, 8320u, 16384u}) {
+        for (uint32_t cw : {8u, 12u, 16u}) {
+            for (uint32_t stages : {2u, 3u, 4u}) {
+                const uint32_t sb = (bytes + 127) / 128 * 128;
+                if ((size_t) sb * stages * cw > 220 * 1024) continue;
+                float best = 1e9;
+                const uint32_t nb = bytes / 4096 * 0 + (uint32_t)(((size_t) gib << 30) / bytes);
+                for (int rep = 0; rep < 4; rep++) {
+                    cudaEventRecord(e0);
+                    read_tma_warp_kernel<<<prop.multiProcessorCount, cw * 32, sb * stages * cw>>>(buf, nb, bytes, bytes, stages, sink);
+                    cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+                    best = fminf(best, time_ms(e0, e1));
+                }
+                printf("read_tma_warp bytes=%5u warps=%2u stages=%u (%3u KB in ring): %8.1f GB/s\n", bytes, cw, stages, sb * stages * cw / 1024, (double) nb * bytes / best / 1e6);
+            }
         }
     }
     const int iters = 4096;
