@@ -5,10 +5,24 @@ NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -cudart stati
 CSRC   := gpusimilarity_b200/csrc
 LIB    := gpusimilarity_b200/libgpusim_b200.so
 
-all: $(LIB) oracle
+all: $(LIB) adapter oracle
 
-$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh include/gpusim_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu
+$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/fsim_reader.cpp include/gpusim_b200.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp -lz
+
+# gpusim::FingerprintDB adapter (the reference's C++ surface over the C ABI).  Qt5 is not installed
+# in this image, so this target compile-checks and tests it against the header-only Qt stand-ins
+# in oracle/qt_shims; with real Qt, build it with -I<Qt include dirs> instead.
+ADAPTER := gpusimilarity_b200/libgpusim_adapter.so
+$(ADAPTER): $(CSRC)/fingerprintdb_adapter.cpp include/gpusim/fingerprintdb_cuda.h include/gpusim/calculation_functors.h $(LIB)
+	g++ -std=c++14 -O2 -fPIC -Wall -Werror -shared -Iinclude -Ioracle/qt_shims -o $@ $(CSRC)/fingerprintdb_adapter.cpp \
+	    -Lgpusimilarity_b200 -lgpusim_b200 -Wl,-rpath,'$$ORIGIN'
+
+tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER)
+	g++ -std=c++14 -O2 -Wall -Iinclude -Ioracle/qt_shims -o $@ tests/cpp/test_adapter.cpp \
+	    -Lgpusimilarity_b200 -lgpusim_adapter -lgpusim_b200 -Wl,-rpath,'$$ORIGIN/../../gpusimilarity_b200'
+
+adapter: $(ADAPTER) tests/cpp/test_adapter
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_api.o $(CSRC)/gsb_api.cu
@@ -19,4 +33,4 @@ oracle:
 clean:
 	rm -f $(LIB)
 	$(MAKE) -C oracle clean
-.PHONY: all oracle clean ptxas-info
+.PHONY: all oracle clean ptxas-info adapter

@@ -52,6 +52,18 @@ SIGNATURES = {
     "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
     "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
+    "gsb_fsim_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
+    "gsb_fsim_close": (None, [_P]),
+    "gsb_fsim_last_error": (C.c_char_p, []),
+    "gsb_fsim_dbkey": (C.c_char_p, [_P]),
+    "gsb_fsim_fp_bits": (C.c_int, [_P]),
+    "gsb_fsim_fp_count": (C.c_uint64, [_P]),
+    "gsb_fsim_chunk_count": (C.c_int, [_P]),
+    "gsb_fsim_chunk_data": (_P, [_P, C.c_int]),
+    "gsb_fsim_chunk_bytes": (C.c_uint64, [_P, C.c_int]),
+    "gsb_fsim_string_count": (C.c_uint64, [_P, C.c_int]),
+    "gsb_fsim_string": (C.c_char_p, [_P, C.c_int, C.c_uint64]),
+    "gsb_fsim_create_db": (C.c_int, [_P, C.POINTER(_P)]),
     "gsb_fold_fingerprint": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "gsb_db_scan_info": (C.c_int, [_P, C.c_int, C.c_uint32, C.POINTER(ScanInfo)]),
     "gsb_selftest_division": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),

@@ -121,6 +121,24 @@ int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint
                      int n_lists, uint32_t list_stride, uint32_t k, uint32_t* d_out_rows,
                      float* d_out_scores, uint32_t* d_out_n);
 
+/* ---- .fsim ingest without Qt (reference GPUSimServer::extractData, gpusim.cpp:173-253, and the
+ * Decompress*Runnable helpers :48-85): big-endian QDataStream framing, qUncompress = zlib after a
+ * 4-byte length, chunks inflated in parallel.  Strings stay valid until gsb_fsim_close. ---- */
+typedef struct gsb_fsim gsb_fsim;
+int gsb_fsim_open(const char* path, gsb_fsim** out);  /* GSB_ERR_IO: unreadable / wrong version */
+void gsb_fsim_close(gsb_fsim* f);
+const char* gsb_fsim_last_error(void);
+const char* gsb_fsim_dbkey(const gsb_fsim* f);
+int gsb_fsim_fp_bits(const gsb_fsim* f);
+uint64_t gsb_fsim_fp_count(const gsb_fsim* f);
+int gsb_fsim_chunk_count(const gsb_fsim* f);
+const void* gsb_fsim_chunk_data(const gsb_fsim* f, int chunk);
+uint64_t gsb_fsim_chunk_bytes(const gsb_fsim* f, int chunk);
+uint64_t gsb_fsim_string_count(const gsb_fsim* f, int which);          /* which: 0 SMILES, 1 ids */
+const char* gsb_fsim_string(const gsb_fsim* f, int which, uint64_t index);
+/* gsb_db_create over the file's fingerprint chunks. */
+int gsb_fsim_create_db(const gsb_fsim* f, gsb_db** out);
+
 /* ---- folding (reference calculation_functors.cpp:22-41, fingerprintdb_cuda.cpp:56-69) ---- */
 int gsb_fold_fingerprint(const int32_t* words, int n_words, int factor, int32_t* out_words);
 
