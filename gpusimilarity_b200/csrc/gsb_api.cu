@@ -224,8 +224,8 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
             std::max<uint64_t>(static_cast<uint64_t>(k) + 4ull * unroll * threads, k + (uint64_t) grid);
         const uint32_t cap = std::max<uint32_t>(pow2ceil(need), static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));
         for (int st = want; st >= 2; st--) {
-            const uint64_t smem =
-                static_cast<uint64_t>(warps) * st * l.stage_bytes + static_cast<uint64_t>(cap) * 8;
+            const uint64_t smem = static_cast<uint64_t>(warps) * st * l.stage_bytes +
+                                  static_cast<uint64_t>(cap) * 8 + gsb::kBuckets * 4;
             if (smem <= static_cast<uint64_t>(budget)) {
                 out->grid = grid;
                 out->warps = warps;
@@ -447,9 +447,44 @@ int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, f
         p.out_keys = sh.ws.out_dev;
         p.out_survivors = sh.ws.out_dev + k;
         p.out_n = reinterpret_cast<uint32_t*>(sh.ws.out_dev + k + 1);
+        unsigned long long* dbg = nullptr;
+        if (env_int("GSB_DEBUG_TIMES", 0)) {
+            GSB_CUDA(cudaMalloc(&dbg, plans[i].grid * 64));
+            GSB_CUDA(cudaMemsetAsync(dbg, 0, plans[i].grid * 64, sh.ws.stream));
+            p.dbg = dbg;
+        }
         rc = launch_scan(db->layout, p, plans[i], sh.ws.stream);
         if (rc)
             return rc;
+        if (dbg) { // developer aid: phase timeline of the launch (ns since the earliest CTA start)
+            std::vector<unsigned long long> h(plans[i].grid * 8);
+            GSB_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost, sh.ws.stream));
+            GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+            cudaFree(dbg);
+            unsigned long long t0 = ~0ull;
+            for (int c = 0; c < plans[i].grid; c++)
+                t0 = std::min(t0, h[c * 8]);
+            const char* names[7] = {"start", "first data", "warp0 out of work", "cta out of work", "final select",
+                                    "ticket", "merge done"};
+            for (int s = 0; s < 7; s++) {
+                unsigned long long lo = ~0ull, hi = 0;
+                double sum = 0;
+                int n = 0;
+                for (int c = 0; c < plans[i].grid; c++) {
+                    const unsigned long long v = h[c * 8 + s];
+                    if (!v)
+                        continue;
+                    lo = std::min(lo, v - t0), hi = std::max(hi, v - t0), sum += double(v - t0), n++;
+                }
+                if (n)
+                    std::fprintf(stderr, "[gsb dbg] %-18s n=%3d min %8.1f us avg %8.1f us max %8.1f us\n", names[s], n,
+                                 lo / 1e3, sum / n / 1e3, hi / 1e3);
+            }
+            unsigned long long emax = 0;
+            for (int c = 0; c < plans[i].grid; c++)
+                emax = std::max(emax, h[c * 8 + 7]);
+            std::fprintf(stderr, "[gsb dbg] selects per CTA during the scan: max %llu\n", emax);
+        }
         GSB_CUDA(cudaMemcpyAsync(sh.ws.out_host, sh.ws.out_dev, (static_cast<size_t>(k) + 2) * 8,
                                  cudaMemcpyDeviceToHost, sh.ws.stream));
     }
@@ -939,7 +974,7 @@ int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint
         return fail(GSB_ERR_INVALID, "null argument");
     GSB_CUDA(cudaSetDevice(device));
     const uint32_t cap = std::max<uint32_t>(4096, pow2ceil(static_cast<uint64_t>(k) + 32ull * n_lists));
-    const size_t smem = static_cast<size_t>(cap) * 8;
+    const size_t smem = static_cast<size_t>(cap) * 8 + gsb::kBuckets * 4;
     int smem_max = 0;
     int rc = smem_limit(device, &smem_max);
     if (rc)
