@@ -7,8 +7,14 @@ LIB    := gpusimilarity_b200/libgpusim_b200.so
 
 all: $(LIB) adapter oracle
 
-$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/fsim_reader.cpp include/gpusim_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp -lz
+$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp include/gpusim_b200.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp -lz
+
+# gpusimserver without Qt: same command line as the reference's main.cpp (--cpu_only, --gpu_bitcount)
+SERVER := gpusimilarity_b200/gpusimserver_b200
+$(SERVER): $(CSRC)/gpusimserver_main.cpp $(LIB)
+	g++ -std=c++14 -O2 -Wall -Iinclude -o $@ $(CSRC)/gpusimserver_main.cpp -Lgpusimilarity_b200 -lgpusim_b200 \
+	    -Wl,-rpath,'$$ORIGIN'
 
 # gpusim::FingerprintDB adapter (the reference's C++ surface over the C ABI).  Qt5 is not installed
 # in this image, so this target compile-checks and tests it against the header-only Qt stand-ins
@@ -22,7 +28,7 @@ tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER)
 	g++ -std=c++14 -O2 -Wall -Iinclude -Ioracle/qt_shims -o $@ tests/cpp/test_adapter.cpp \
 	    -Lgpusimilarity_b200 -lgpusim_adapter -lgpusim_b200 -Wl,-rpath,'$$ORIGIN/../../gpusimilarity_b200'
 
-adapter: $(ADAPTER) tests/cpp/test_adapter
+adapter: $(ADAPTER) tests/cpp/test_adapter $(SERVER)
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_api.o $(CSRC)/gsb_api.cu

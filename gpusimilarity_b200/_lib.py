@@ -64,6 +64,19 @@ SIGNATURES = {
     "gsb_fsim_string_count": (C.c_uint64, [_P, C.c_int]),
     "gsb_fsim_string": (C.c_char_p, [_P, C.c_int, C.c_uint64]),
     "gsb_fsim_create_db": (C.c_int, [_P, C.POINTER(_P)]),
+    "gsb_server_create": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "gsb_server_destroy": (None, [_P]),
+    "gsb_server_last_error": (C.c_char_p, []),
+    "gsb_server_set_use_gpu": (None, [_P, C.c_int]),
+    "gsb_server_using_gpu": (C.c_int, [_P]),
+    "gsb_server_fold_factor": (C.c_uint, [_P]),
+    "gsb_server_database_count": (C.c_int, [_P]),
+    "gsb_server_get_fingerprint": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P]),
+    "gsb_server_handle_request": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint64)]),
+    "gsb_server_free": (None, [_P]),
+    "gsb_server_listen": (C.c_int, [_P, C.c_char_p]),
+    "gsb_server_serve": (C.c_int, [_P, C.c_uint64]),
+    "gsb_server_stop": (None, [_P]),
     "gsb_fold_fingerprint": (C.c_int, [_P, C.c_int, C.c_int, _P]),
     "gsb_db_scan_info": (C.c_int, [_P, C.c_int, C.c_uint32, C.POINTER(ScanInfo)]),
     "gsb_selftest_division": (C.c_int, [C.c_int, C.POINTER(C.c_uint64)]),

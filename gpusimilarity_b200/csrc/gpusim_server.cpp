@@ -1,0 +1,456 @@
+// Qt-free equivalent of the reference's GPUSimServer (gpusim.h:23-95, gpusim.cpp:87-461): load
+// .fsim databases, pick the fold factor, answer similarity searches over the local socket
+// "gpusimilarity" with the reference's QDataStream wire format, merge several databases and
+// de-duplicate identical SMILES.  Host-side only; all scoring goes through the C ABI.
+//
+// Wire format (big-endian QDataStream, default stream version => `float` travels as an 8-byte
+// double):
+//   request : i32 n_db; n_db x (cstr dbname, cstr dbkey); i32 request_num; i32 results_requested;
+//             f64 cutoff; QByteArray fingerprint                      (gpusim.cpp:384-414)
+//   response: i32 request_num; i32 n; u64 approximate_count;
+//             n x cstr smiles; n x cstr ids; n x f64 score            (gpusim.cpp:431-453)
+#include "../../include/gpusim_b200.h"
+
+#include <poll.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace
+{
+thread_local std::string g_srv_err;
+
+struct Database {
+    std::string name, key;
+    gsb_fsim* file = nullptr; // owns the SMILES / id strings
+    gsb_db* db = nullptr;
+    ~Database()
+    {
+        gsb_db_destroy(db);
+        gsb_fsim_close(file);
+    }
+};
+
+struct Result {
+    float score;
+    const char* smiles;
+    const char* id;
+};
+
+// ---- QDataStream primitives -------------------------------------------------------------
+struct Reader {
+    const uint8_t* p;
+    size_t n, off = 0;
+    bool ok = true;
+    bool need(size_t k)
+    {
+        if (off + k > n)
+            ok = false;
+        return ok;
+    }
+    uint32_t u32()
+    {
+        if (!need(4))
+            return 0;
+        const uint8_t* q = p + off;
+        off += 4;
+        return (uint32_t(q[0]) << 24) | (uint32_t(q[1]) << 16) | (uint32_t(q[2]) << 8) | uint32_t(q[3]);
+    }
+    int32_t i32() { return static_cast<int32_t>(u32()); }
+    double f64()
+    {
+        if (!need(8))
+            return 0;
+        uint64_t v = 0;
+        for (int i = 0; i < 8; i++)
+            v = (v << 8) | p[off + i];
+        off += 8;
+        double d;
+        std::memcpy(&d, &v, 8);
+        return d;
+    }
+    std::string bytes()
+    {
+        uint32_t len = u32();
+        if (len == 0xFFFFFFFFu)
+            len = 0;
+        if (!need(len))
+            return std::string();
+        std::string s(reinterpret_cast<const char*>(p + off), len);
+        off += len;
+        return s;
+    }
+    std::string cstr()
+    {
+        std::string s = bytes();
+        if (!s.empty() && s.back() == '\0')
+            s.pop_back();
+        return s;
+    }
+};
+
+struct Writer {
+    std::vector<uint8_t> buf;
+    void u32(uint32_t v)
+    {
+        for (int s = 24; s >= 0; s -= 8)
+            buf.push_back(static_cast<uint8_t>(v >> s));
+    }
+    void u64(uint64_t v)
+    {
+        for (int s = 56; s >= 0; s -= 8)
+            buf.push_back(static_cast<uint8_t>(v >> s));
+    }
+    void f64(double d)
+    {
+        uint64_t v;
+        std::memcpy(&v, &d, 8);
+        u64(v);
+    }
+    void cstr(const char* s)
+    {
+        const size_t len = std::strlen(s) + 1;
+        u32(static_cast<uint32_t>(len));
+        buf.insert(buf.end(), s, s + len);
+    }
+};
+
+std::string base_name(const std::string& path)
+{
+    // QFileInfo::baseName(): file name up to (not including) the first '.'
+    const size_t slash = path.find_last_of('/');
+    const std::string file = slash == std::string::npos ? path : path.substr(slash + 1);
+    return file.substr(0, file.find('.'));
+}
+} // namespace
+
+struct gsb_server {
+    std::map<std::string, std::unique_ptr<Database>> dbs; // QHash in the reference; order is irrelevant there
+    bool use_gpu = true;
+    unsigned fold_factor = 1;
+    int listen_fd = -1;
+    std::string socket_path;
+    std::atomic<bool> stop{false};
+
+    bool using_gpu() const { return use_gpu && gsb_device_count() != 0; } // gpusim.cpp:168-171
+
+    // GPUSimServer::similaritySearch (gpusim.cpp:276-293) on one database, results as pointers
+    int similarity_search(Database& d, const int32_t* q, int n_words, const std::string& key, unsigned k,
+                          float cutoff, bool gpu, std::vector<Result>* out, uint64_t* approx)
+    {
+        *approx = 0;
+        if (key != d.key) // fingerprintdb_cuda.cu:349-352: silently empty
+            return GSB_OK;
+        std::vector<uint32_t> rows(k ? k : 1);
+        std::vector<float> scores(rows.size());
+        uint32_t n = 0;
+        int rc;
+        if (gpu)
+            rc = gsb_db_search(d.db, q, n_words, k, cutoff, rows.data(), scores.data(), &n, approx);
+        else
+            rc = gsb_db_search_cpu(d.db, q, n_words, k, rows.data(), scores.data(), &n);
+        if (rc != GSB_OK) {
+            g_srv_err = gsb_last_error();
+            return rc;
+        }
+        for (uint32_t i = 0; i < n; i++)
+            out->push_back({scores[i], gsb_fsim_string(d.file, 0, rows[i]), gsb_fsim_string(d.file, 1, rows[i])});
+        return GSB_OK;
+    }
+
+    // GPUSimServer::searchDatabases (gpusim.cpp:306-374)
+    int search_databases(const int32_t* q, int n_words, int results_requested, float cutoff,
+                         const std::vector<std::pair<std::string, std::string>>& name_key,
+                         std::vector<std::string>* smiles, std::vector<std::string>* ids, std::vector<float>* scores,
+                         uint64_t* approx_total)
+    {
+        std::map<std::string, std::string> ordered(name_key.begin(), name_key.end()); // std::map<QString,QString>
+        std::vector<Result> all;
+        for (const auto& nk : ordered) {
+            auto it = dbs.find(nk.first);
+            if (it == dbs.end()) // "Unknown database requested": skipped (:322-325)
+                continue;
+            uint64_t approx = 0;
+            const int rc = similarity_search(*it->second, q, n_words, nk.second,
+                                             static_cast<unsigned>(std::max(results_requested, 0)), cutoff, using_gpu(),
+                                             &all, &approx);
+            if (rc != GSB_OK)
+                return rc;
+            *approx_total += approx; // :332
+        }
+        // :339-340 sort + reverse = descending score; ties keep (database, rank) order here, the
+        // reference breaks them by pointer value
+        std::stable_sort(all.begin(), all.end(), [](const Result& a, const Result& b) { return a.score > b.score; });
+        std::map<std::string, std::string> smiles_to_ids; // :342-359
+        for (const Result& r : all) {
+            auto it = smiles_to_ids.find(r.smiles);
+            if (it != smiles_to_ids.end())
+                it->second += std::string(";:;") + r.id;
+            else
+                smiles_to_ids[r.smiles] = r.id;
+            if (smiles_to_ids.size() >= static_cast<size_t>(std::max(results_requested, 0)))
+                break;
+        }
+        std::set<std::string> written; // :361-373
+        int count = 0;
+        for (const Result& r : all) {
+            if (count >= results_requested)
+                break;
+            if (!written.insert(r.smiles).second)
+                continue;
+            scores->push_back(r.score);
+            smiles->push_back(r.smiles);
+            ids->push_back(smiles_to_ids[r.smiles]);
+            count++;
+        }
+        return GSB_OK;
+    }
+
+    // GPUSimServer::incomingSearchRequest (gpusim.cpp:376-454) without the socket
+    int handle_request(const uint8_t* data, size_t len, std::vector<uint8_t>* response)
+    {
+        Reader rd{data, len};
+        const int n_db = rd.i32();
+        std::vector<std::pair<std::string, std::string>> name_key;
+        for (int i = 0; i < n_db && rd.ok; i++) {
+            std::string name = rd.cstr();
+            std::string key = rd.cstr();
+            name_key.emplace_back(name, key);
+        }
+        const int request_num = rd.i32();
+        const int results_requested = rd.i32();
+        const float cutoff = static_cast<float>(rd.f64());
+        const std::string fp = rd.bytes();
+        if (!rd.ok) {
+            g_srv_err = "truncated request";
+            return GSB_ERR_INVALID;
+        }
+        std::vector<int32_t> query(fp.size() / 4);
+        std::memcpy(query.data(), fp.data(), query.size() * 4);
+        std::vector<std::string> smiles, ids;
+        std::vector<float> scores;
+        uint64_t approx = 0;
+        const int rc = search_databases(query.data(), static_cast<int>(query.size()), results_requested, cutoff,
+                                        name_key, &smiles, &ids, &scores, &approx);
+        if (rc != GSB_OK)
+            return rc;
+        Writer w;
+        w.u32(static_cast<uint32_t>(request_num));
+        w.u32(static_cast<uint32_t>(smiles.size()));
+        w.u64(approx);
+        for (const auto& s : smiles)
+            w.cstr(s.c_str());
+        for (const auto& s : ids)
+            w.cstr(s.c_str());
+        for (float s : scores)
+            w.f64(static_cast<double>(s));
+        response->swap(w.buf);
+        return GSB_OK;
+    }
+};
+
+extern "C" {
+
+const char* gsb_server_last_error(void) { return g_srv_err.c_str(); }
+
+int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcount, int use_gpu, gsb_server** out)
+{
+    if (!out || n_paths < 0 || (n_paths > 0 && !fsim_paths)) {
+        g_srv_err = "null argument";
+        return GSB_ERR_INVALID;
+    }
+    std::unique_ptr<gsb_server> srv(new gsb_server);
+    srv->use_gpu = use_gpu != 0;
+    uint64_t total_db_memory = 0, max_compounds = 0;
+    int max_bitcount = 0;
+    for (int i = 0; i < n_paths; i++) { // gpusim.cpp:97-117
+        std::unique_ptr<Database> d(new Database);
+        int rc = gsb_fsim_open(fsim_paths[i], &d->file);
+        if (rc != GSB_OK) {
+            g_srv_err = gsb_fsim_last_error();
+            return rc;
+        }
+        rc = gsb_fsim_create_db(d->file, &d->db);
+        if (rc != GSB_OK) {
+            g_srv_err = gsb_last_error();
+            return rc;
+        }
+        d->name = base_name(fsim_paths[i]);
+        d->key = gsb_fsim_dbkey(d->file);
+        total_db_memory += gsb_db_data_bytes(d->db);
+        max_compounds = std::max<uint64_t>(max_compounds, gsb_db_count(d->db));
+        max_bitcount = std::max(max_bitcount, gsb_db_fp_bits(d->db));
+        srv->dbs[d->name] = std::move(d);
+    }
+    // fold-factor policy, gpusim.cpp:131-151
+    unsigned fold_factor = 1;
+    if (gsb_device_count() > 0) {
+        uint64_t gpu_memory = gsb_available_device_bytes();
+        const uint64_t reserve = sizeof(int) * max_compounds;
+        gpu_memory = gpu_memory > reserve ? gpu_memory - reserve : 0;
+        if (total_db_memory > gpu_memory && gpu_memory > 0)
+            fold_factor = static_cast<unsigned>(std::ceil(static_cast<float>(total_db_memory) /
+                                                          static_cast<float>(gpu_memory)));
+    }
+    if (gpu_bitcount > 0) {
+        const unsigned arg_fold_factor = static_cast<unsigned>(max_bitcount / gpu_bitcount);
+        if (arg_fold_factor < fold_factor) {
+            g_srv_err = "GPU bitset not sufficiently small to fit on GPU";
+            return GSB_ERR_INVALID;
+        }
+        fold_factor = std::max(1u, arg_fold_factor);
+    }
+    srv->fold_factor = fold_factor;
+    if (srv->using_gpu()) { // gpusim.cpp:159-163
+        for (auto& kv : srv->dbs) {
+            const int rc = gsb_db_upload(kv.second->db, nullptr, 0, fold_factor);
+            if (rc != GSB_OK) {
+                g_srv_err = gsb_last_error();
+                return rc;
+            }
+        }
+    }
+    *out = srv.release();
+    return GSB_OK;
+}
+
+void gsb_server_destroy(gsb_server* srv)
+{
+    if (!srv)
+        return;
+    if (srv->listen_fd >= 0) {
+        close(srv->listen_fd);
+        unlink(srv->socket_path.c_str());
+    }
+    delete srv;
+}
+
+void gsb_server_set_use_gpu(gsb_server* srv, int use_gpu) { srv->use_gpu = use_gpu != 0; } // gpusim.h:82
+int gsb_server_using_gpu(const gsb_server* srv) { return srv->using_gpu() ? 1 : 0; }
+unsigned gsb_server_fold_factor(const gsb_server* srv) { return srv->fold_factor; }
+int gsb_server_database_count(const gsb_server* srv) { return static_cast<int>(srv->dbs.size()); }
+
+// GPUSimServer::getFingerprint (gpusim.cpp:456-459)
+int gsb_server_get_fingerprint(const gsb_server* srv, const char* dbname, uint64_t row, int32_t* out_words)
+{
+    auto it = srv->dbs.find(dbname);
+    if (it == srv->dbs.end()) {
+        g_srv_err = "unknown database";
+        return GSB_ERR_INVALID;
+    }
+    const int rc = gsb_db_get_fingerprint(it->second->db, row, out_words);
+    if (rc != GSB_OK)
+        g_srv_err = gsb_last_error();
+    return rc;
+}
+
+// One request in the reference wire format -> one response.  *response is malloc'ed; free with
+// gsb_server_free.
+int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t request_bytes, void** response,
+                              uint64_t* response_bytes)
+{
+    std::vector<uint8_t> out;
+    const int rc = srv->handle_request(static_cast<const uint8_t*>(request), request_bytes, &out);
+    if (rc != GSB_OK)
+        return rc;
+    *response = std::malloc(out.size() ? out.size() : 1);
+    std::memcpy(*response, out.data(), out.size());
+    *response_bytes = out.size();
+    return GSB_OK;
+}
+
+void gsb_server_free(void* p) { std::free(p); }
+
+// GPUSimServer::setupSocket (gpusim.cpp:255-274): listen on <dir>/<name> ("/tmp/gpusimilarity"),
+// removing a stale socket file once.
+int gsb_server_listen(gsb_server* srv, const char* socket_path)
+{
+    srv->socket_path = socket_path && *socket_path ? socket_path : "/tmp/gpusimilarity";
+    sockaddr_un addr{};
+    addr.sun_family = AF_UNIX;
+    std::snprintf(addr.sun_path, sizeof(addr.sun_path), "%s", srv->socket_path.c_str());
+    for (int attempt = 0; attempt < 2; attempt++) {
+        const int fd = socket(AF_UNIX, SOCK_STREAM, 0);
+        if (fd < 0)
+            break;
+        if (bind(fd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0 && listen(fd, 16) == 0) {
+            srv->listen_fd = fd;
+            return GSB_OK;
+        }
+        close(fd);
+        unlink(srv->socket_path.c_str());
+    }
+    g_srv_err = "Server start failed on " + srv->socket_path;
+    return GSB_ERR_IO;
+}
+
+void gsb_server_stop(gsb_server* srv) { srv->stop = true; }
+
+// Event loop: one request in flight at a time, like the reference's Qt main thread.  Returns
+// after gsb_server_stop() or after max_requests (0 = unlimited) were answered.
+int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
+{
+    if (srv->listen_fd < 0) {
+        g_srv_err = "not listening";
+        return GSB_ERR_STATE;
+    }
+    std::vector<pollfd> fds{{srv->listen_fd, POLLIN, 0}};
+    std::map<int, std::vector<uint8_t>> pending;
+    uint64_t served = 0;
+    while (!srv->stop && (max_requests == 0 || served < max_requests)) {
+        if (poll(fds.data(), fds.size(), 100) <= 0)
+            continue;
+        if (fds[0].revents & POLLIN) {
+            const int c = accept(srv->listen_fd, nullptr, nullptr);
+            if (c >= 0)
+                fds.push_back({c, POLLIN, 0});
+        }
+        for (size_t i = 1; i < fds.size();) {
+            if (!(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) {
+                i++;
+                continue;
+            }
+            uint8_t chunk[65536];
+            const ssize_t got = read(fds[i].fd, chunk, sizeof(chunk));
+            if (got <= 0) {
+                close(fds[i].fd);
+                pending.erase(fds[i].fd);
+                fds.erase(fds.begin() + i);
+                continue;
+            }
+            auto& buf = pending[fds[i].fd];
+            buf.insert(buf.end(), chunk, chunk + got);
+            std::vector<uint8_t> response;
+            const int rc = srv->handle_request(buf.data(), buf.size(), &response);
+            if (rc == GSB_OK) {
+                size_t sent = 0;
+                while (sent < response.size()) {
+                    const ssize_t w = write(fds[i].fd, response.data() + sent, response.size() - sent);
+                    if (w <= 0)
+                        break;
+                    sent += static_cast<size_t>(w);
+                }
+                buf.clear();
+                served++;
+            } else if (g_srv_err != "truncated request") {
+                buf.clear(); // malformed or failed search: drop it, keep the connection
+            }
+            i++;
+        }
+    }
+    return GSB_OK;
+}
+
+} // extern "C"

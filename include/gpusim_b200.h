@@ -139,6 +139,34 @@ const char* gsb_fsim_string(const gsb_fsim* f, int which, uint64_t index);
 /* gsb_db_create over the file's fingerprint chunks. */
 int gsb_fsim_create_db(const gsb_fsim* f, gsb_db** out);
 
+/* ---- serving (reference GPUSimServer, gpusim.h:23-95 / gpusim.cpp:87-461), without Qt ----
+ * Loads the .fsim files (database name = file base name, gpusim.cpp:114-116), applies the
+ * fold-factor policy (:121-151; gpu_bitcount = 0 means automatic; GSB_ERR_INVALID "GPU bitset not
+ * sufficiently small to fit on GPU" like the reference's std::invalid_argument), uploads when a
+ * GPU is used (:159-163).  use_gpu = 0 is --cpu_only (main.cpp:21-28,64-65). */
+typedef struct gsb_server gsb_server;
+int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcount, int use_gpu,
+                      gsb_server** out);
+void gsb_server_destroy(gsb_server* srv);
+const char* gsb_server_last_error(void);
+void gsb_server_set_use_gpu(gsb_server* srv, int use_gpu);   /* setUseGPU, gpusim.h:82          */
+int gsb_server_using_gpu(const gsb_server* srv);             /* usingGPU, gpusim.cpp:168-171    */
+unsigned gsb_server_fold_factor(const gsb_server* srv);
+int gsb_server_database_count(const gsb_server* srv);
+int gsb_server_get_fingerprint(const gsb_server* srv, const char* dbname, uint64_t row,
+                               int32_t* out_words);          /* getFingerprint, gpusim.cpp:456-459 */
+/* incomingSearchRequest (gpusim.cpp:376-454) on a byte buffer: parse the reference's request,
+ * run searchDatabases (:306-374: per-database search, merge, SMILES de-duplication with ids joined
+ * by ";:;"), serialise the reference's response.  *response is malloc'ed: gsb_server_free. */
+int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t request_bytes,
+                              void** response, uint64_t* response_bytes);
+void gsb_server_free(void* p);
+/* setupSocket (gpusim.cpp:255-274): unix socket, default "/tmp/gpusimilarity" (what QLocalServer
+ * name "gpusimilarity" resolves to); then the one-request-at-a-time event loop. */
+int gsb_server_listen(gsb_server* srv, const char* socket_path);
+int gsb_server_serve(gsb_server* srv, uint64_t max_requests);
+void gsb_server_stop(gsb_server* srv);
+
 /* ---- folding (reference calculation_functors.cpp:22-41, fingerprintdb_cuda.cpp:56-69) ---- */
 int gsb_fold_fingerprint(const int32_t* words, int n_words, int factor, int32_t* out_words);
 
