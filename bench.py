@@ -214,7 +214,8 @@ def main():
     q_pinned = torch.from_numpy(query_np.copy()).pin_memory()
     d_query = q_pinned.to(dev)
     stream = torch.cuda.current_stream()
-    searcher = ShardedSearcher(db, K, local_rank, dist, world)
+    fused = os.environ.get("GSB_FUSED_EXCHANGE", "1") != "0"
+    searcher = ShardedSearcher(db, K, local_rank, dist, world, rank=rank, fused=fused)
 
     def device_step(q_ptr):
         """scan (1 launch) [+ all-gather + merge (1 launch) when sharded]; results stay in HBM."""
@@ -308,7 +309,9 @@ def main():
                 "grid": info.grid, "block": info.block, "tma_stages_per_warp": info.stages, "tma_bytes_per_copy": info.tile_bytes,
                 "layout_bytes_per_query": info.db_bytes_per_query,
                 "smem_bytes": info.smem_bytes, "synthetic_gen_s": round(t_gen, 2),
-                "parallelism": f"row-sharded x{world}" + (", NCCL all-gather of per-shard top-k + merge kernel" if world > 1 else ""),
+                "parallelism": f"row-sharded x{world}" + (
+                    "" if world == 1 else (", fused in-kernel exchange of per-shard top-k over NVLink peer memory"
+                                           if searcher.fused else ", NCCL all-gather of per-shard top-k + merge kernel")),
             },
             "e2e": {"value": args.steps / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": 128 * world, "d2h_bytes_per_step": (K + 2) * 8 if world == 1 else K * 8 + 4,
@@ -334,5 +337,30 @@ def main():
         dist.destroy_process_group()
 
 
+def _main_with_clean_stdout():
+    """stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner,
+    for one) are sent to stderr for the duration of the run."""
+    import io
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    captured = io.StringIO()
+    real_stdout, sys.stdout = sys.stdout, captured
+    try:
+        main()
+    finally:
+        sys.stdout = real_stdout
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    lines = [l for l in captured.getvalue().splitlines() if l.strip()]
+    json_lines = [l for l in lines if l.lstrip().startswith("{")]
+    for l in lines:
+        if l not in json_lines:
+            print(l, file=sys.stderr)
+    if json_lines:
+        print(json_lines[-1], flush=True)
+
+
 if __name__ == "__main__":
-    main()
+    _main_with_clean_stdout()

@@ -18,6 +18,10 @@ class GsbError(RuntimeError):
         self.code = code
 
 
+class Exchange(C.Structure):
+    _fields_ = [("peer_base", C.c_uint64 * 16), ("rank", C.c_uint32), ("world", C.c_uint32), ("seq", C.c_uint64)]
+
+
 class ScanInfo(C.Structure):
     _fields_ = [("device", C.c_int), ("grid", C.c_int), ("block", C.c_int), ("stages", C.c_int),
                 ("tile_rows", C.c_uint32), ("tile_bytes", C.c_uint32), ("smem_bytes", C.c_uint32),
@@ -51,6 +55,8 @@ SIGNATURES = {
     "gsb_db_search_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint32, C.c_float, _P, _P, _P, _P]),
     "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
+    "gsb_exchange_bytes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
+    "gsb_db_search_device_fused": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, C.POINTER(Exchange), _P, _P, _P, _P]),
     "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "gsb_fsim_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "gsb_fsim_close": (None, [_P]),

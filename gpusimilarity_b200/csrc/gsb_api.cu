@@ -967,6 +967,50 @@ int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query,
     return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
 }
 
+int gsb_exchange_bytes(uint32_t world, uint32_t k, uint64_t* bytes)
+{
+    if (!bytes || world == 0 || world > gsb::kMaxRanks || k == 0)
+        return fail(GSB_ERR_INVALID, "bad exchange geometry");
+    *bytes = (gsb::xchg_flag_offset(1, world, world - 1, k) + 8 + 255) / 256 * 256;
+    return GSB_OK;
+}
+
+int gsb_db_search_device_fused(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k, float cutoff,
+                               const gsb_exchange* xchg, uint32_t* d_out_rows, float* d_out_scores,
+                               uint32_t* d_out_n, uint64_t* d_out_approx)
+{
+    if (!db || !d_query || !xchg || !d_out_rows || !d_out_scores || !d_out_n || !d_out_approx || k == 0)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (xchg->world < 2 || xchg->world > gsb::kMaxRanks || xchg->rank >= xchg->world || xchg->seq == 0)
+        return fail(GSB_ERR_INVALID, "bad exchange descriptor");
+    if (!db->uploaded || db->shards.size() != 1)
+        return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
+    if (db->fold_factor != 1)
+        return fail(GSB_ERR_STATE, "device search does not re-score folded databases");
+    Shard& sh = const_cast<Shard&>(db->shards[0]);
+    Plan plan;
+    int rc = make_plan(db->layout, sh, k, &plan);
+    if (rc)
+        return rc;
+    rc = ws_reserve(sh, k, plan.grid, false);
+    if (rc)
+        return rc;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    gsb::ScanParams p;
+    fill_params(db, sh, plan, k, cutoff, &p);
+    p.q_dev = reinterpret_cast<const uint32_t*>(d_query);
+    p.out_n = d_out_n;
+    p.out_survivors = reinterpret_cast<unsigned long long*>(d_out_approx);
+    p.out_rows = d_out_rows;
+    p.out_scores = d_out_scores;
+    p.x_world = xchg->world;
+    p.x_rank = xchg->rank;
+    p.x_seq = xchg->seq;
+    for (uint32_t r = 0; r < xchg->world; r++)
+        p.x_peer[r] = xchg->peer_base[r];
+    return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
+}
+
 int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint32_t* d_counts, int n_lists,
                      uint32_t list_stride, uint32_t k, uint32_t* d_out_rows, float* d_out_scores, uint32_t* d_out_n)
 {

@@ -45,9 +45,11 @@ def exchange_candidates(record, world: int, dist):
 class ShardedSearcher:
     """This rank's shard of a database plus the buffers of the per-query exchange."""
 
-    def __init__(self, db, k: int, local_device: int, dist=None, world: int = 1):
+    def __init__(self, db, k: int, local_device: int, dist=None, world: int = 1, rank: int = 0,
+                 fused: bool = False):
         import torch
         self.torch, self.db, self.k, self.dist, self.world = torch, db, k, dist, world
+        self.rank, self.fused, self.seq = rank, False, 0
         self.device_index = local_device
         dev = torch.device("cuda", local_device)
         self.rec = torch.zeros(k + RECORD_EXTRA, dtype=torch.int64, device=dev)
@@ -58,6 +60,35 @@ class ShardedSearcher:
         self.h_rows = torch.zeros(k, dtype=torch.int32).pin_memory()
         self.h_scores = torch.zeros(k, dtype=torch.float32).pin_memory()
         self.h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.out_approx = torch.zeros(1, dtype=torch.int64, device=dev)
+        if fused and world > 1:
+            self._setup_fused(dev)
+
+    def _setup_fused(self, dev) -> None:
+        """Exchange buffers in NVLink peer-mapped (symmetric) memory for the one-launch query path
+        (gsb_db_search_device_fused).  Falls back to the NCCL all-gather path if the platform cannot
+        map peer memory; both are product paths."""
+        import ctypes as C
+        import torch
+        from ._lib import Exchange, check, lib
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            nbytes = C.c_uint64(0)
+            check(lib().gsb_exchange_bytes(self.world, self.k, C.byref(nbytes)))
+            self.xbuf = symm_mem.empty(int(nbytes.value), dtype=torch.uint8, device=dev)
+            self.xbuf.zero_()
+            hdl = symm_mem.rendezvous(self.xbuf, self.dist.group.WORLD)
+            self.xchg = Exchange()
+            for r in range(self.world):
+                self.xchg.peer_base[r] = int(hdl.buffer_ptrs[r])
+            self.xchg.rank, self.xchg.world = self.rank, self.world
+            torch.cuda.synchronize()
+            self.dist.barrier()          # every buffer is zeroed before anybody stores into it
+            self.fused = True
+        except Exception as e:  # pragma: no cover - depends on the platform
+            import sys
+            print(f"[gpusimilarity_b200] fused exchange unavailable ({e!r}); using NCCL all-gather", file=sys.stderr)
+            self.fused = False
 
     def search_local(self, d_query_ptr: int, cutoff: float, stream) -> None:
         """One fused scan+select launch over this rank's shard; the record stays in HBM."""
@@ -69,6 +100,16 @@ class ShardedSearcher:
         """Scan, exchange, merge — all asynchronous on ``stream``; results stay in HBM
         (out_rows / out_scores / out_n)."""
         from .fingerprintdb import merge_device
+        if self.fused:
+            import ctypes as C
+            from ._lib import check, lib
+            self.seq += 1
+            self.xchg.seq = self.seq
+            check(lib().gsb_db_search_device_fused(self.db._h, stream.cuda_stream, d_query_ptr, self.k, cutoff,
+                                                   C.byref(self.xchg), self.out_rows.data_ptr(),
+                                                   self.out_scores.data_ptr(), self.out_n.data_ptr(),
+                                                   self.out_approx.data_ptr()))
+            return
         self.search_local(d_query_ptr, cutoff, stream)
         if self.world > 1:
             self.dist.all_gather_into_tensor(self.gathered, self.rec)
@@ -80,6 +121,8 @@ class ShardedSearcher:
                      self.out_n.data_ptr())
 
     def approx_count(self) -> int:
+        if self.fused:
+            return int(self.out_approx.item())
         src = self.gathered if self.world > 1 else self.rec
         return int(src.view(self.world if self.world > 1 else 1, self.k + RECORD_EXTRA)[:, self.k].sum().item())
 

@@ -121,6 +121,24 @@ int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint
                      int n_lists, uint32_t list_stride, uint32_t k, uint32_t* d_out_rows,
                      float* d_out_scores, uint32_t* d_out_n);
 
+/* Fused scan + cross-GPU exchange + merge in ONE launch per rank: the last CTA of every rank's
+ * scan stores its shard's candidate record straight into every rank's exchange buffer through
+ * NVLink peer-mapped memory, raises an arrival flag there, waits for all ranks' flags in its own
+ * buffer and merges.  Every rank ends with the global top-k (rows, scores, count, approximate
+ * count) in its own device buffers; no NCCL call and no second launch on the query path.
+ * peer_base[r] is rank r's exchange buffer as mapped into THIS process (e.g. torch symmetric
+ * memory `buffer_ptrs`), gsb_exchange_bytes() large and zero-filled before the first query.
+ * seq is the query number: 1, 2, 3, ... identical on all ranks. */
+typedef struct gsb_exchange {
+    uint64_t peer_base[16];
+    uint32_t rank, world;
+    uint64_t seq;
+} gsb_exchange;
+int gsb_exchange_bytes(uint32_t world, uint32_t k, uint64_t* bytes);
+int gsb_db_search_device_fused(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k,
+                               float cutoff, const gsb_exchange* xchg, uint32_t* d_out_rows,
+                               float* d_out_scores, uint32_t* d_out_n, uint64_t* d_out_approx);
+
 /* ---- .fsim ingest without Qt (reference GPUSimServer::extractData, gpusim.cpp:173-253, and the
  * Decompress*Runnable helpers :48-85): big-endian QDataStream framing, qUncompress = zlib after a
  * 4-byte length, chunks inflated in parallel.  Strings stay valid until gsb_fsim_close. ---- */

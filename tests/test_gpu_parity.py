@@ -328,6 +328,60 @@ def test_device_entry_points_and_merge_kernel():
         assert_same(got, OC.c_search(q_np, whole_np, k, cutoff), f"3 shards cutoff={cutoff}")
 
 
+def test_fused_peer_exchange_two_ranks_on_one_gpu(monkeypatch):
+    """gsb_db_search_device_fused with two 'ranks' in one process: two shards, two streams, small
+    grids so that both launches are resident at once; the exchange buffers are plain device
+    allocations here (on the 8-GPU box they are NVLink peer mappings)."""
+    import ctypes as C
+    import torch
+    from gpusimilarity_b200._lib import Exchange, check, lib
+    from gpusimilarity_b200.dist import shard_range
+    monkeypatch.setenv("GSB_GRID", "12")
+    n, k, seed, plant, world = 600_000, 1000, 33, 500, 2
+    whole_np = OC.c_synth_db(seed, n, 32, plant)
+    dev = torch.device("cuda", 0)
+    nbytes = C.c_uint64(0)
+    check(lib().gsb_exchange_bytes(world, k, C.byref(nbytes)))
+    xbufs = [torch.zeros(nbytes.value, dtype=torch.uint8, device=dev) for _ in range(world)]
+    shards, outs, streams = [], [], []
+    for r in range(world):
+        base, rows = shard_range(n, r, world)
+        shards.append(gsb.FingerprintDB.synthetic(rows, device=0, seed=seed, plant_period=plant, row_base=base))
+        outs.append((torch.zeros(k, dtype=torch.int32, device=dev), torch.zeros(k, dtype=torch.float32, device=dev),
+                     torch.zeros(1, dtype=torch.int32, device=dev), torch.zeros(1, dtype=torch.int64, device=dev)))
+        streams.append(torch.cuda.Stream())
+    # allocate every shard's workspace up front: cudaMalloc inside the first search would wait
+    # for the other rank's spinning kernel (one process, one GPU here)
+    warm = torch.zeros(k + 2, dtype=torch.int64, device=dev)
+    d_q0 = torch.from_numpy(O.synth_template(seed, 32).copy()).to(dev)
+    for r in range(world):
+        shards[r].search_device(0, d_q0.data_ptr(), k, 0.0, warm.data_ptr(), warm.data_ptr() + 8 * (k + 1),
+                                warm.data_ptr() + 8 * k)
+    torch.cuda.synchronize()
+    seq = 0
+    for q_np, cutoff in ((O.synth_template(seed, 32), 0.0), (whole_np[77], 0.0), (O.synth_template(seed, 32), 0.3),
+                         (whole_np[599_999], 0.05)):
+        seq += 1
+        d_q = torch.from_numpy(np.ascontiguousarray(q_np)).to(dev)
+        torch.cuda.synchronize()
+        for r in range(world):
+            x = Exchange()
+            for j in range(world):
+                x.peer_base[j] = xbufs[j].data_ptr()
+            x.rank, x.world, x.seq = r, world, seq
+            o = outs[r]
+            check(lib().gsb_db_search_device_fused(shards[r]._h, streams[r].cuda_stream, d_q.data_ptr(), k, cutoff,
+                                                   C.byref(x), o[0].data_ptr(), o[1].data_ptr(), o[2].data_ptr(),
+                                                   o[3].data_ptr()))
+        torch.cuda.synchronize()
+        want = OC.c_search(q_np, whole_np, k, cutoff)
+        for r in range(world):
+            o = outs[r]
+            cnt = int(o[2].item())
+            got = (o[0][:cnt].cpu().numpy().astype(np.int64) & 0xffffffff, o[1][:cnt].cpu().numpy(), int(o[3].item()))
+            assert_same(got, want, f"fused rank {r} seq {seq}")
+
+
 def test_errors_are_loud():
     rows_np = O.synth_db(1, 1000, 32, 0)
     db = gsb.FingerprintDB(1024, 1000, "pass", [rows_np])
