@@ -71,9 +71,12 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50",
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
+            t_end = time.time() + 3.0          # nvidia-smi needs a moment before its first sample
+            while not self.lines and time.time() < t_end:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
@@ -88,7 +91,12 @@ class ClockSampler:
         self.proc.terminate()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.06] or [l for (_, l) in self.lines]
+        # samples inside the load window; a window shorter than the sampling period falls back to
+        # the nearest samples around it (the GPU is under the same load during warm-up)
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1 + 0.03]
+        if len(rows) < 3:
+            near = sorted(self.lines, key=lambda tl: abs(tl[0] - (t0 + t1) / 2))[:5]
+            rows = [l for (_, l) in near]
         for line in rows:
             f = [x.strip() for x in line.split(",")]
             try:
@@ -253,7 +261,6 @@ def main():
     t_wall1 = time.time()
     launches = gsb.launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
-    clocks = sampler.stop(t_wall0, t_wall1)
 
     # ---- the scan kernel alone (roofline): one event pair per launch, same stream
     kern_ms = []
@@ -274,7 +281,9 @@ def main():
         res = e2e_step()
         t_e2e.append(time.perf_counter() - t)
     barrier()
+    t_wall2 = time.time()
     e2e_ms = sum(t_e2e) * 1e3
+    clocks = sampler.stop(t_wall0, t_wall2)   # all three timed regions keep the GPU under the same load
 
     # max over ranks
     if dist is not None:

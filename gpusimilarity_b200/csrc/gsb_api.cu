@@ -341,47 +341,48 @@ int upload_rows(const gsb_db* db, Shard& sh)
     GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
     GSB_CUDA(cudaMemsetAsync(sh.tiles, 0, sh.bytes, sh.ws.stream));
 
+    // Pipelined ingest: pieces of the host rows go through two pinned staging buffers (host
+    // threads copy into one while the other is on the wire), land in device staging, and one kernel
+    // folds (reference FoldFingerprintFunctorCPU, calculation_functors.cpp:22-41 — "port folding to
+    // the GPU" is on the reference's own to-do list), zero-pads to the device row width, writes the
+    // 32-row batches and their popcount trailers.  The reference copies from pageable memory
+    // (.cu:181-182) after folding on the CPU (fingerprintdb_cuda.cpp:56-69).
     const uint32_t src_words = db->words;
-    const bool direct = db->fold_factor == 1 && l.dev_words == src_words;
-    const uint32_t* src = nullptr;
-    std::vector<uint32_t> staged;
-    if (direct) {
-        src = db->host.data() + sh.row_base * src_words;
-    } else {
-        staged.assign(static_cast<size_t>(sh.n_rows) * l.dev_words, 0u);
-        const uint32_t f = db->fold_factor;
-        const uint32_t* base = db->host.data() + sh.row_base * src_words;
-        uint32_t* dst = staged.data();
-        const uint32_t dw = l.dev_words, fw = src_words / f;
-        parallel_for(sh.n_rows, [=](uint64_t lo, uint64_t hi) {
-            std::vector<uint32_t> tmp(fw);
-            for (uint64_t r = lo; r < hi; r++) {
-                fold_row(base + r * src_words, src_words, f, tmp.data());
-                std::memcpy(dst + r * dw, tmp.data(), fw * 4);
-            }
-        });
-        src = staged.data();
+    const uint32_t f = db->fold_factor;
+    const uint64_t src_row_bytes = static_cast<uint64_t>(src_words) * 4;
+    const uint64_t piece_rows = std::max<uint64_t>(32, ((64ull << 20) / src_row_bytes) / 32 * 32);
+    uint8_t* pinned[2] = {nullptr, nullptr};
+    uint8_t* staged[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    for (int i = 0; i < 2; i++) {
+        GSB_CUDA(cudaMallocHost(&pinned[i], piece_rows * src_row_bytes));
+        GSB_CUDA(cudaMalloc(&staged[i], piece_rows * src_row_bytes));
+        GSB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     }
-    const size_t tile_row_bytes = static_cast<size_t>(l.tile_rows) * l.row_bytes;
-    if (!l.rowpop) {
-        GSB_CUDA(cudaMemcpyAsync(sh.tiles, src, static_cast<size_t>(sh.n_rows) * l.row_bytes,
-                                 cudaMemcpyHostToDevice, sh.ws.stream));
-    } else {
-        const uint64_t full = sh.n_rows / l.tile_rows;
-        if (full)
-            GSB_CUDA(cudaMemcpy2DAsync(sh.tiles, l.tile_stride, src, tile_row_bytes, tile_row_bytes, full,
-                                       cudaMemcpyHostToDevice, sh.ws.stream));
-        const uint64_t rest = sh.n_rows - full * l.tile_rows;
-        if (rest)
-            GSB_CUDA(cudaMemcpyAsync(sh.tiles + full * l.tile_stride,
-                                     reinterpret_cast<const uint8_t*>(src) + full * tile_row_bytes,
-                                     rest * l.row_bytes, cudaMemcpyHostToDevice, sh.ws.stream));
-        const uint64_t rows = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows;
-        if (rows) {
-            gsb::tile_popcount_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, sh.ws.stream>>>(
-                sh.tiles, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words);
-            g_launches++;
-        }
+    const uint8_t* base = reinterpret_cast<const uint8_t*>(db->host.data() + sh.row_base * src_words);
+    int slot = 0;
+    for (uint64_t r0 = 0; r0 < sh.n_rows; r0 += piece_rows, slot ^= 1) {
+        const uint64_t rows = std::min<uint64_t>(piece_rows, sh.n_rows - r0);
+        GSB_CUDA(cudaEventSynchronize(done[slot])); // the previous use of this slot has been consumed
+        const uint8_t* src = base + r0 * src_row_bytes;
+        uint8_t* dst = pinned[slot];
+        parallel_for(rows, [=](uint64_t lo, uint64_t hi) {
+            std::memcpy(dst + lo * src_row_bytes, src + lo * src_row_bytes, (hi - lo) * src_row_bytes);
+        });
+        GSB_CUDA(cudaMemcpyAsync(staged[slot], pinned[slot], rows * src_row_bytes, cudaMemcpyHostToDevice,
+                                 sh.ws.stream));
+        const uint64_t threads = rows * l.dev_words;
+        gsb::ingest_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, sh.ws.stream>>>(
+            reinterpret_cast<const uint32_t*>(staged[slot]), rows, r0, src_words, f, sh.tiles, l.tile_stride,
+            l.dev_words, l.rowpop ? 1 : 0);
+        g_launches++;
+        GSB_CUDA(cudaEventRecord(done[slot], sh.ws.stream));
+    }
+    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+    for (int i = 0; i < 2; i++) {
+        cudaFreeHost(pinned[i]);
+        cudaFree(staged[i]);
+        cudaEventDestroy(done[i]);
     }
     GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
     GSB_CUDA(cudaGetLastError());
