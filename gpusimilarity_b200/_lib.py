@@ -55,6 +55,8 @@ SIGNATURES = {
     "gsb_db_search_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint32, C.c_float, _P, _P, _P, _P]),
     "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
+    "gsb_db_search_batch_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_float, _P, _P, _P]),
+    "gsb_merge_batch_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_uint32, _P, _P, _P, _P]),
     "gsb_exchange_bytes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gsb_db_search_device_fused": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, C.POINTER(Exchange), _P, _P, _P, _P]),
     "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
@@ -80,6 +82,8 @@ SIGNATURES = {
     "gsb_server_get_fingerprint": (C.c_int, [_P, C.c_char_p, C.c_uint64, _P]),
     "gsb_server_handle_request": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "gsb_server_free": (None, [_P]),
+    "gsb_server_handle_batch": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.c_int, C.POINTER(_P),
+                                          C.POINTER(C.c_uint64)]),
     "gsb_server_listen": (C.c_int, [_P, C.c_char_p]),
     "gsb_server_serve": (C.c_int, [_P, C.c_uint64]),
     "gsb_server_stop": (None, [_P]),

@@ -190,6 +190,14 @@ struct gsb_server {
                 return rc;
             *approx_total += approx; // :332
         }
+        merge_and_dedup(all, results_requested, smiles, ids, scores);
+        return GSB_OK;
+    }
+
+    // the merge half of searchDatabases (gpusim.cpp:339-373)
+    static void merge_and_dedup(std::vector<Result>& all, int results_requested, std::vector<std::string>* smiles,
+                                std::vector<std::string>* ids, std::vector<float>* scores)
+    {
         // :339-340 sort + reverse = descending score; ties keep (database, rank) order here, the
         // reference breaks them by pointer value
         std::stable_sort(all.begin(), all.end(), [](const Result& a, const Result& b) { return a.score > b.score; });
@@ -215,39 +223,41 @@ struct gsb_server {
             ids->push_back(smiles_to_ids[r.smiles]);
             count++;
         }
-        return GSB_OK;
     }
 
-    // GPUSimServer::incomingSearchRequest (gpusim.cpp:376-454) without the socket
-    int handle_request(const uint8_t* data, size_t len, std::vector<uint8_t>* response)
+    struct Request {
+        std::vector<std::pair<std::string, std::string>> name_key;
+        int request_num = 0, results_requested = 0;
+        float cutoff = 0;
+        std::vector<int32_t> query;
+    };
+
+    static bool parse_request(const uint8_t* data, size_t len, Request* r)
     {
         Reader rd{data, len};
         const int n_db = rd.i32();
-        std::vector<std::pair<std::string, std::string>> name_key;
         for (int i = 0; i < n_db && rd.ok; i++) {
             std::string name = rd.cstr();
             std::string key = rd.cstr();
-            name_key.emplace_back(name, key);
+            r->name_key.emplace_back(name, key);
         }
-        const int request_num = rd.i32();
-        const int results_requested = rd.i32();
-        const float cutoff = static_cast<float>(rd.f64());
+        r->request_num = rd.i32();
+        r->results_requested = rd.i32();
+        r->cutoff = static_cast<float>(rd.f64());
         const std::string fp = rd.bytes();
-        if (!rd.ok) {
-            g_srv_err = "truncated request";
-            return GSB_ERR_INVALID;
-        }
-        std::vector<int32_t> query(fp.size() / 4);
-        std::memcpy(query.data(), fp.data(), query.size() * 4);
-        std::vector<std::string> smiles, ids;
-        std::vector<float> scores;
-        uint64_t approx = 0;
-        const int rc = search_databases(query.data(), static_cast<int>(query.size()), results_requested, cutoff,
-                                        name_key, &smiles, &ids, &scores, &approx);
-        if (rc != GSB_OK)
-            return rc;
+        if (!rd.ok)
+            return false;
+        r->query.resize(fp.size() / 4);
+        std::memcpy(r->query.data(), fp.data(), r->query.size() * 4);
+        return true;
+    }
+
+    static void write_response(const Request& r, const std::vector<std::string>& smiles,
+                               const std::vector<std::string>& ids, const std::vector<float>& scores, uint64_t approx,
+                               std::vector<uint8_t>* response)
+    {
         Writer w;
-        w.u32(static_cast<uint32_t>(request_num));
+        w.u32(static_cast<uint32_t>(r.request_num));
         w.u32(static_cast<uint32_t>(smiles.size()));
         w.u64(approx);
         for (const auto& s : smiles)
@@ -257,6 +267,71 @@ struct gsb_server {
         for (float s : scores)
             w.f64(static_cast<double>(s));
         response->swap(w.buf);
+    }
+
+    // GPUSimServer::incomingSearchRequest (gpusim.cpp:376-454) without the socket
+    int handle_request(const uint8_t* data, size_t len, std::vector<uint8_t>* response)
+    {
+        Request r;
+        if (!parse_request(data, len, &r)) {
+            g_srv_err = "truncated request";
+            return GSB_ERR_INVALID;
+        }
+        std::vector<std::string> smiles, ids;
+        std::vector<float> scores;
+        uint64_t approx = 0;
+        const int rc = search_databases(r.query.data(), static_cast<int>(r.query.size()), r.results_requested, r.cutoff,
+                                        r.name_key, &smiles, &ids, &scores, &approx);
+        if (rc != GSB_OK)
+            return rc;
+        write_response(r, smiles, ids, scores, approx, response);
+        return GSB_OK;
+    }
+
+    // Requests that arrived together and ask the same thing of the same databases (same names and
+    // keys, result count, cutoff, query width) are answered from ONE gsb_db_search_batch call per
+    // database, i.e. one pass over the database for all of them.  The reference serves strictly
+    // one query at a time (python/gpusim_server.py:32,100-121 holds a mutex around the socket).
+    int handle_batch(const std::vector<const Request*>& group, std::vector<std::vector<uint8_t>>* responses)
+    {
+        const Request& first = *group[0];
+        const size_t nq = group.size();
+        const int n_words = static_cast<int>(first.query.size());
+        const unsigned k = static_cast<unsigned>(std::max(first.results_requested, 0));
+        std::map<std::string, std::string> ordered(first.name_key.begin(), first.name_key.end());
+        std::vector<std::vector<Result>> all(nq);
+        std::vector<uint64_t> approx_total(nq, 0);
+        std::vector<int32_t> queries(nq * n_words);
+        for (size_t q = 0; q < nq; q++)
+            std::memcpy(queries.data() + q * n_words, group[q]->query.data(), n_words * 4);
+        for (const auto& nk : ordered) {
+            auto it = dbs.find(nk.first);
+            if (it == dbs.end() || nk.second != it->second->key)
+                continue;
+            Database& d = *it->second;
+            std::vector<uint32_t> rows(nq * std::max(k, 1u)), cnt(nq);
+            std::vector<float> scores(rows.size());
+            std::vector<uint64_t> approx(nq);
+            const int rc = gsb_db_search_batch(d.db, queries.data(), n_words, static_cast<int>(nq), k, first.cutoff,
+                                               rows.data(), scores.data(), cnt.data(), approx.data());
+            if (rc != GSB_OK) {
+                g_srv_err = gsb_last_error();
+                return rc;
+            }
+            for (size_t q = 0; q < nq; q++) {
+                approx_total[q] += approx[q];
+                for (uint32_t i = 0; i < cnt[q]; i++)
+                    all[q].push_back({scores[q * k + i], gsb_fsim_string(d.file, 0, rows[q * k + i]),
+                                      gsb_fsim_string(d.file, 1, rows[q * k + i])});
+            }
+        }
+        responses->resize(nq);
+        for (size_t q = 0; q < nq; q++) {
+            std::vector<std::string> smiles, ids;
+            std::vector<float> scores;
+            merge_and_dedup(all[q], first.results_requested, &smiles, &ids, &scores);
+            write_response(*group[q], smiles, ids, scores, approx_total[q], &(*responses)[q]);
+        }
         return GSB_OK;
     }
 };
@@ -373,6 +448,46 @@ int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t req
 
 void gsb_server_free(void* p) { std::free(p); }
 
+// n requests that ask the same thing (same databases and keys, result count, cutoff, query width),
+// answered from one gsb_db_search_batch call per database.  responses[i] is malloc'ed.
+int gsb_server_handle_batch(gsb_server* srv, const void* const* requests, const uint64_t* request_bytes, int n,
+                            void** responses, uint64_t* response_bytes)
+{
+    if (n <= 0 || !requests || !request_bytes || !responses || !response_bytes) {
+        g_srv_err = "null argument";
+        return GSB_ERR_INVALID;
+    }
+    std::vector<gsb_server::Request> parsed(n);
+    std::vector<const gsb_server::Request*> group;
+    for (int i = 0; i < n; i++) {
+        if (!gsb_server::parse_request(static_cast<const uint8_t*>(requests[i]), request_bytes[i], &parsed[i])) {
+            g_srv_err = "truncated request";
+            return GSB_ERR_INVALID;
+        }
+        const auto &x = parsed[0], &y = parsed[i];
+        if (x.name_key != y.name_key || x.results_requested != y.results_requested || x.cutoff != y.cutoff ||
+            x.query.size() != y.query.size()) {
+            g_srv_err = "requests of one batch must ask the same thing";
+            return GSB_ERR_INVALID;
+        }
+        group.push_back(&parsed[i]);
+    }
+    if (!srv->using_gpu()) {
+        g_srv_err = "batched search needs the GPU path";
+        return GSB_ERR_STATE;
+    }
+    std::vector<std::vector<uint8_t>> out;
+    const int rc = srv->handle_batch(group, &out);
+    if (rc != GSB_OK)
+        return rc;
+    for (int i = 0; i < n; i++) {
+        responses[i] = std::malloc(out[i].size() ? out[i].size() : 1);
+        std::memcpy(responses[i], out[i].data(), out[i].size());
+        response_bytes[i] = out[i].size();
+    }
+    return GSB_OK;
+}
+
 // GPUSimServer::setupSocket (gpusim.cpp:255-274): listen on <dir>/<name> ("/tmp/gpusimilarity"),
 // removing a stale socket file once.
 int gsb_server_listen(gsb_server* srv, const char* socket_path)
@@ -409,6 +524,15 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
     std::vector<pollfd> fds{{srv->listen_fd, POLLIN, 0}};
     std::map<int, std::vector<uint8_t>> pending;
     uint64_t served = 0;
+    auto send_all = [](int fd, const std::vector<uint8_t>& buf) {
+        size_t sent = 0;
+        while (sent < buf.size()) {
+            const ssize_t w = write(fd, buf.data() + sent, buf.size() - sent);
+            if (w <= 0)
+                break;
+            sent += static_cast<size_t>(w);
+        }
+    };
     while (!srv->stop && (max_requests == 0 || served < max_requests)) {
         if (poll(fds.data(), fds.size(), 100) <= 0)
             continue;
@@ -417,6 +541,8 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
             if (c >= 0)
                 fds.push_back({c, POLLIN, 0});
         }
+        // read what is there; every connection with a complete request joins this round
+        std::vector<std::pair<int, gsb_server::Request>> ready;
         for (size_t i = 1; i < fds.size();) {
             if (!(fds[i].revents & (POLLIN | POLLHUP | POLLERR))) {
                 i++;
@@ -432,22 +558,50 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
             }
             auto& buf = pending[fds[i].fd];
             buf.insert(buf.end(), chunk, chunk + got);
-            std::vector<uint8_t> response;
-            const int rc = srv->handle_request(buf.data(), buf.size(), &response);
-            if (rc == GSB_OK) {
-                size_t sent = 0;
-                while (sent < response.size()) {
-                    const ssize_t w = write(fds[i].fd, response.data() + sent, response.size() - sent);
-                    if (w <= 0)
-                        break;
-                    sent += static_cast<size_t>(w);
-                }
+            gsb_server::Request r;
+            if (gsb_server::parse_request(buf.data(), buf.size(), &r)) {
+                ready.emplace_back(fds[i].fd, std::move(r));
                 buf.clear();
-                served++;
-            } else if (g_srv_err != "truncated request") {
-                buf.clear(); // malformed or failed search: drop it, keep the connection
             }
             i++;
+        }
+        // group identical "shapes" and answer each group from one batched search
+        std::vector<bool> taken(ready.size(), false);
+        for (size_t a = 0; a < ready.size(); a++) {
+            if (taken[a])
+                continue;
+            std::vector<size_t> members{a};
+            for (size_t b = a + 1; b < ready.size(); b++) {
+                const auto &x = ready[a].second, &y = ready[b].second;
+                if (!taken[b] && x.name_key == y.name_key && x.results_requested == y.results_requested &&
+                    x.cutoff == y.cutoff && x.query.size() == y.query.size())
+                    members.push_back(b);
+            }
+            for (size_t m : members)
+                taken[m] = true;
+            if (members.size() >= 2 && srv->using_gpu()) {
+                std::vector<const gsb_server::Request*> group;
+                for (size_t m : members)
+                    group.push_back(&ready[m].second);
+                std::vector<std::vector<uint8_t>> responses;
+                if (srv->handle_batch(group, &responses) == GSB_OK)
+                    for (size_t g = 0; g < members.size(); g++)
+                        send_all(ready[members[g]].first, responses[g]);
+            } else {
+                for (size_t m : members) {
+                    const auto& r = ready[m].second;
+                    std::vector<std::string> smiles, ids;
+                    std::vector<float> scores;
+                    uint64_t approx = 0;
+                    std::vector<uint8_t> response;
+                    if (srv->search_databases(r.query.data(), static_cast<int>(r.query.size()), r.results_requested,
+                                              r.cutoff, r.name_key, &smiles, &ids, &scores, &approx) == GSB_OK) {
+                        gsb_server::write_response(r, smiles, ids, scores, approx, &response);
+                        send_all(ready[m].first, response);
+                    }
+                }
+            }
+            served += members.size();
         }
     }
     return GSB_OK;

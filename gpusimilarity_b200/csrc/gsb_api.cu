@@ -5,6 +5,7 @@
 //   FingerprintDB ctor / copyToGPU / search / search_storage / getFingerprint
 //   (fingerprintdb_cuda.cu:117-381), search_cpu / fold_data (fingerprintdb_cuda.cpp:20-69),
 //   get_gpu_count / get_next_gpu / get_available_gpu_memory (fingerprintdb_cuda.cu:33-68,401-413).
+#include "gsb_batch.cuh"
 #include "gsb_kernels.cuh"
 
 #include "../../include/gpusim_b200.h"
@@ -99,6 +100,17 @@ struct Workspace {
     unsigned long long* out_host = nullptr; // pinned
     uint32_t out_cap = 0;                   // keys
     int max_grid = 0;
+    // multi-query kernel scratch (allocated on first use)
+    gsb::BatchCtrl* bctrl = nullptr;
+    unsigned long long* bcand = nullptr;   // [grid][kMaxBatchQueries][kBatchListCap]
+    unsigned long long* bqlists = nullptr; // [grid][kMaxBatchQueries][bk_cap]
+    uint32_t* bqcounts = nullptr;
+    unsigned long long* bsurv = nullptr;
+    uint32_t* bqueries = nullptr;          // [kMaxBatchQueries][dev_words]
+    unsigned long long* bout = nullptr;    // [kMaxBatchQueries][bk_cap + 2] results (+ survivors, n)
+    unsigned long long* bout_host = nullptr;
+    uint32_t bk_cap = 0;
+    int bgrid = 0;
 };
 
 struct Shard {
@@ -293,6 +305,15 @@ void ws_free(Shard& sh)
     cudaFree(ws.out_dev);
     if (ws.out_host)
         cudaFreeHost(ws.out_host);
+    cudaFree(ws.bctrl);
+    cudaFree(ws.bcand);
+    cudaFree(ws.bqlists);
+    cudaFree(ws.bqcounts);
+    cudaFree(ws.bsurv);
+    cudaFree(ws.bqueries);
+    cudaFree(ws.bout);
+    if (ws.bout_host)
+        cudaFreeHost(ws.bout_host);
     cudaFree(sh.tiles);
     sh = Shard();
 }
@@ -562,6 +583,219 @@ int scan_topk(const gsb_db* db, const uint32_t* q_dev_words, uint64_t k_total, f
         if (pass.size() < want)
             break; // the database is exhausted
         ceiling = pass.back();
+    }
+    return GSB_OK;
+}
+
+// ---- multi-query kernel ------------------------------------------------------------------
+bool batch_kernel_applies(const gsb_db* db, uint32_t k, int n_queries)
+{
+    return db->layout.rowpop && db->layout.dev_words <= 32 && db->fold_factor == 1 && k >= 1 &&
+           k <= gsb::kMaxBatchK && n_queries >= 2 && env_int("GSB_BATCH_KERNEL", 1) != 0;
+}
+
+struct BatchPlan {
+    int grid = 0, warps = 16;
+    uint32_t stages = 2, smem = 0;
+};
+
+int make_batch_plan(const Layout& l, const Shard& sh, BatchPlan* out)
+{
+    int smem_max = 0;
+    int rc = smem_limit(sh.device, &smem_max);
+    if (rc)
+        return rc;
+    const uint64_t fixed = static_cast<uint64_t>(gsb::kMaxBatchQueries) * l.dev_words * 4 + gsb::kBatchListCap * 8ull +
+                           gsb::kBuckets * 4ull + gsb::kMaxBatchQueries * (8ull + 8 + 4 + 4);
+    for (int warps = 16; warps >= 8; warps -= 8) {
+        const uint64_t smem = static_cast<uint64_t>(warps) * 2 * l.stage_bytes + fixed;
+        if (smem + 2048 <= static_cast<uint64_t>(smem_max)) {
+            out->warps = warps;
+            out->stages = 2;
+            out->smem = static_cast<uint32_t>(smem);
+            int sms = 0;
+            GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+            const uint32_t n_super = (sh.n_tiles + warps - 1) / warps;
+            out->grid = std::max(1, std::min<int>(sms, n_super ? n_super : 1)); // all CTAs resident: grid barrier
+            if (const int g = env_int("GSB_GRID", 0))
+                out->grid = std::max(1, std::min(out->grid, g));
+            return GSB_OK;
+        }
+    }
+    return fail(GSB_ERR_INVALID, "no batch launch shape fits");
+}
+
+int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid)
+{
+    Workspace& ws = sh.ws;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    if (!ws.bctrl) {
+        GSB_CUDA(cudaMalloc(&ws.bctrl, sizeof(gsb::BatchCtrl)));
+        GSB_CUDA(cudaMemset(ws.bctrl, 0, sizeof(gsb::BatchCtrl)));
+        GSB_CUDA(cudaMalloc(&ws.bsurv, gsb::kMaxBatchQueries * 8));
+        GSB_CUDA(cudaMemset(ws.bsurv, 0, gsb::kMaxBatchQueries * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqueries, static_cast<size_t>(gsb::kMaxBatchQueries) * l.dev_words * 4));
+    }
+    if (grid > ws.bgrid || k > ws.bk_cap) {
+        cudaFree(ws.bcand);
+        cudaFree(ws.bqlists);
+        cudaFree(ws.bqcounts);
+        cudaFree(ws.bout);
+        if (ws.bout_host)
+            cudaFreeHost(ws.bout_host);
+        ws.bcand = ws.bqlists = ws.bout = ws.bout_host = nullptr;
+        ws.bqcounts = nullptr;
+        const int g = std::max(grid, ws.bgrid);
+        const uint32_t kc = std::max(k, ws.bk_cap);
+        const size_t nq = gsb::kMaxBatchQueries;
+        GSB_CUDA(cudaMalloc(&ws.bcand, static_cast<size_t>(g) * nq * gsb::kBatchListCap * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqlists, static_cast<size_t>(g) * nq * kc * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqcounts, static_cast<size_t>(g) * nq * 4));
+        GSB_CUDA(cudaMalloc(&ws.bout, nq * (kc + 2ull) * 8));
+        GSB_CUDA(cudaMallocHost(&ws.bout_host, nq * (kc + 2ull) * 8));
+        ws.bgrid = g;
+        ws.bk_cap = kc;
+    }
+    return GSB_OK;
+}
+
+template <int W> int launch_batch_t(const gsb::BatchParams& p, const BatchPlan& plan, cudaStream_t st)
+{
+    auto go = [&](auto kernel) -> int {
+        GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
+        // cooperative launch: the runtime refuses the launch unless every CTA can be resident,
+        // which the grid-wide arrival counter in the kernel relies on
+        void* args[] = {const_cast<gsb::BatchParams*>(&p)};
+        GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(plan.grid), dim3(plan.warps * 32),
+                                             args, plan.smem, st));
+        g_launches++;
+        return GSB_OK;
+    };
+    return plan.warps == 16 ? go(gsb::scan_batch_kernel<W, 16>) : go(gsb::scan_batch_kernel<W, 8>);
+}
+
+int launch_batch(const Layout& l, const gsb::BatchParams& p, const BatchPlan& plan, cudaStream_t st)
+{
+    switch (l.dev_words) {
+    case 4:
+        return launch_batch_t<4>(p, plan, st);
+    case 8:
+        return launch_batch_t<8>(p, plan, st);
+    case 16:
+        return launch_batch_t<16>(p, plan, st);
+    case 32:
+        return launch_batch_t<32>(p, plan, st);
+    default:
+        return fail(GSB_ERR_INVALID, "the multi-query kernel handles rows up to 1024 bits");
+    }
+}
+
+// One launch over one shard for nq <= kMaxBatchQueries queries already in device memory.
+// Results: out_keys [nq][k], out_survivors [nq], out_n [nq].
+int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
+                       float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
+{
+    BatchPlan plan;
+    int rc = make_batch_plan(db->layout, sh, &plan);
+    if (rc)
+        return rc;
+    rc = batch_reserve(sh, db->layout, k, plan.grid);
+    if (rc)
+        return rc;
+    const Layout& l = db->layout;
+    gsb::BatchParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.tiles = sh.tiles;
+    p.n_rows = sh.n_rows;
+    p.row_base = sh.row_base;
+    p.n_batches = sh.n_tiles;
+    p.batch_stride = l.tile_stride;
+    p.batch_bytes = l.tile_bytes;
+    p.stage_bytes = l.stage_bytes;
+    p.stages = plan.stages;
+    p.k = k;
+    p.cutoff = cutoff;
+    p.nq = nq;
+    p.queries = d_queries;
+    p.cand = sh.ws.bcand;
+    p.qlists = sh.ws.bqlists;
+    p.qcounts = sh.ws.bqcounts;
+    p.surv_acc = sh.ws.bsurv;
+    p.ctrl = sh.ws.bctrl;
+    p.out_keys = out_keys;
+    p.out_n = out_n;
+    p.out_survivors = out_surv;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    return launch_batch(l, p, plan, st);
+}
+
+// Host-buffer batch over every shard: groups of up to kMaxBatchQueries queries per launch.
+int search_batch_kernel_path(const gsb_db* db, const int32_t* query_words, int n_queries, uint32_t k, float cutoff,
+                             uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+{
+    const Layout& l = db->layout;
+    const uint32_t words = db->words;
+    for (int q0 = 0; q0 < n_queries; q0 += gsb::kMaxBatchQueries) {
+        const uint32_t nq = static_cast<uint32_t>(std::min<int>(gsb::kMaxBatchQueries, n_queries - q0));
+        std::vector<uint32_t> padded(static_cast<size_t>(nq) * l.dev_words, 0u);
+        for (uint32_t j = 0; j < nq; j++)
+            std::memcpy(padded.data() + static_cast<size_t>(j) * l.dev_words,
+                        query_words + static_cast<size_t>(q0 + j) * words, words * 4);
+        for (size_t i = 0; i < db->shards.size(); i++) {
+            Shard& sh = const_cast<Shard&>(db->shards[i]);
+            if (sh.n_rows == 0)
+                continue;
+            BatchPlan plan;
+            int rc = make_batch_plan(l, sh, &plan);
+            if (rc)
+                return rc;
+            rc = batch_reserve(sh, l, k, plan.grid);
+            if (rc)
+                return rc;
+            GSB_CUDA(cudaSetDevice(sh.device));
+            GSB_CUDA(cudaMemcpyAsync(sh.ws.bqueries, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice,
+                                     sh.ws.stream));
+            unsigned long long* keys = sh.ws.bout;
+            unsigned long long* surv = sh.ws.bout + static_cast<size_t>(nq) * k;
+            uint32_t* cnt = reinterpret_cast<uint32_t*>(surv + nq);
+            rc = batch_launch_shard(db, sh, sh.ws.stream, sh.ws.bqueries, nq, k, cutoff, keys, cnt, surv);
+            if (rc)
+                return rc;
+            GSB_CUDA(cudaMemcpyAsync(sh.ws.bout_host, sh.ws.bout, (static_cast<size_t>(nq) * (k + 2ull)) * 8,
+                                     cudaMemcpyDeviceToHost, sh.ws.stream));
+        }
+        std::vector<std::vector<unsigned long long>> merged(nq);
+        std::vector<uint64_t> approx(nq, 0);
+        for (size_t i = 0; i < db->shards.size(); i++) {
+            const Shard& sh = db->shards[i];
+            if (sh.n_rows == 0)
+                continue;
+            GSB_CUDA(cudaSetDevice(sh.device));
+            GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+            const unsigned long long* keys = sh.ws.bout_host;
+            const unsigned long long* surv = keys + static_cast<size_t>(nq) * k;
+            const uint32_t* cnt = reinterpret_cast<const uint32_t*>(surv + nq);
+            for (uint32_t j = 0; j < nq; j++) {
+                approx[j] += surv[j];
+                auto& m = merged[j];
+                const size_t old = m.size();
+                m.insert(m.end(), keys + static_cast<size_t>(j) * k, keys + static_cast<size_t>(j) * k + cnt[j]);
+                std::inplace_merge(m.begin(), m.begin() + old, m.end(), std::greater<unsigned long long>());
+                if (m.size() > k)
+                    m.resize(k);
+            }
+        }
+        for (uint32_t j = 0; j < nq; j++) {
+            const size_t q = static_cast<size_t>(q0) + j;
+            for (size_t i = 0; i < merged[j].size(); i++) {
+                const Cand c = decode(merged[j][i]);
+                out_rows[q * k + i] = c.row;
+                out_scores[q * k + i] = c.score;
+            }
+            out_n[q] = static_cast<uint32_t>(merged[j].size());
+            if (out_approx)
+                out_approx[q] = approx[j];
+        }
     }
     return GSB_OK;
 }
@@ -892,6 +1126,11 @@ int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_word
 {
     if (n_queries < 0)
         return fail(GSB_ERR_INVALID, "negative query count");
+    if (db && query_words && out_rows && out_scores && out_n && db->uploaded &&
+        n_words == static_cast<int>(db->words) && batch_kernel_applies(db, k, n_queries)) {
+        std::lock_guard<std::mutex> lock(db->mu);
+        return search_batch_kernel_path(db, query_words, n_queries, k, cutoff, out_rows, out_scores, out_n, out_approx);
+    }
     for (int qi = 0; qi < n_queries; qi++) {
         int rc = gsb_db_search(db, query_words + static_cast<size_t>(qi) * n_words, n_words, k, cutoff,
                                out_rows + static_cast<size_t>(qi) * k, out_scores + static_cast<size_t>(qi) * k,
@@ -966,6 +1205,44 @@ int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query,
     p.out_n = d_out_n;
     p.out_survivors = reinterpret_cast<unsigned long long*>(d_out_survivors);
     return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
+}
+
+int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_queries, int n_queries, uint32_t k,
+                               float cutoff, gsb_key* d_out_keys, uint32_t* d_out_n, uint64_t* d_out_survivors)
+{
+    if (!db || !d_queries || !d_out_keys || !d_out_n || !d_out_survivors)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (!db->uploaded || db->shards.size() != 1)
+        return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
+    if (n_queries < 1 || n_queries > static_cast<int>(gsb::kMaxBatchQueries))
+        return fail(GSB_ERR_INVALID, "1..256 queries per launch");
+    if (!db->layout.rowpop || db->layout.dev_words > 32 || db->layout.dev_words != db->words || db->fold_factor != 1 ||
+        k < 1 || k > gsb::kMaxBatchK)
+        return fail(GSB_ERR_INVALID, "the multi-query kernel needs the default layout, <= 1024 bits, k <= 512");
+    Shard& sh = const_cast<Shard&>(db->shards[0]);
+    return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_queries),
+                              static_cast<uint32_t>(n_queries), k, cutoff,
+                              reinterpret_cast<unsigned long long*>(d_out_keys), d_out_n,
+                              reinterpret_cast<unsigned long long*>(d_out_survivors));
+}
+
+int gsb_merge_batch_device(int device, void* stream, const gsb_key* d_records, int n_ranks, int n_queries, uint32_t k,
+                           uint32_t* d_out_rows, float* d_out_scores, uint32_t* d_out_n, uint64_t* d_out_approx)
+{
+    if (!d_records || !d_out_rows || !d_out_scores || !d_out_n || !d_out_approx || n_ranks <= 0 || n_queries <= 0 || k == 0)
+        return fail(GSB_ERR_INVALID, "null argument");
+    GSB_CUDA(cudaSetDevice(device));
+    const uint32_t cap = std::max<uint32_t>(4096, pow2ceil(static_cast<uint64_t>(k) + 32ull * n_ranks));
+    const size_t smem = static_cast<size_t>(cap) * 8 + gsb::kBuckets * 4;
+    GSB_CUDA(cudaFuncSetAttribute(gsb::merge_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    gsb::merge_batch_kernel<<<n_queries, gsb::kMergeThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const unsigned long long*>(d_records), static_cast<uint32_t>(n_ranks),
+        static_cast<uint32_t>(n_queries), k, cap, d_out_rows, d_out_scores, d_out_n,
+        reinterpret_cast<unsigned long long*>(d_out_approx));
+    g_launches++;
+    GSB_CUDA(cudaGetLastError());
+    return GSB_OK;
 }
 
 int gsb_exchange_bytes(uint32_t world, uint32_t k, uint64_t* bytes)

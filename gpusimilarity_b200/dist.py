@@ -136,3 +136,39 @@ class ShardedSearcher:
         stream.synchronize()
         n = int(self.h_n[0])
         return self.h_rows[:n].numpy().astype(np.int64) & 0xFFFFFFFF, self.h_scores[:n].numpy().copy()
+
+
+class ShardedBatchSearcher:
+    """Multi-query variant (BASELINE config "1024 queries, top-100, 8 GPUs"): every rank scores its
+    shard against up to 256 queries per launch (gsb_db_search_batch_device), the per-rank records
+    ([nq][k] keys, [nq] survivors, [nq] counts) are all-gathered and merged with one CTA per query."""
+
+    MAX_QUERIES = 256
+
+    def __init__(self, db, k: int, local_device: int, dist=None, world: int = 1):
+        import torch
+        self.torch, self.db, self.k, self.dist, self.world, self.device_index = torch, db, k, dist, world, local_device
+        dev = torch.device("cuda", local_device)
+        nq = self.MAX_QUERIES
+        self.rec = torch.zeros(nq * (k + 2), dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros(world * nq * (k + 2), dtype=torch.int64, device=dev)
+        self.out_rows = torch.zeros(nq * k, dtype=torch.int32, device=dev)
+        self.out_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
+        self.out_n = torch.zeros(nq, dtype=torch.int32, device=dev)
+        self.out_approx = torch.zeros(nq, dtype=torch.int64, device=dev)
+
+    def search_device(self, d_queries_ptr: int, n_queries: int, cutoff: float, stream) -> None:
+        """Results for queries [0, n_queries) stay in HBM: out_rows/out_scores [nq][k], out_n, out_approx."""
+        from ._lib import check, lib
+        nq, k = n_queries, self.k
+        rec_len = nq * (k + 2)
+        p = self.rec.data_ptr()
+        check(lib().gsb_db_search_batch_device(self.db._h, stream.cuda_stream, d_queries_ptr, nq, k, cutoff, p,
+                                               p + 8 * nq * (k + 1), p + 8 * nq * k))
+        src = self.rec
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered[:self.world * rec_len], self.rec[:rec_len])
+            src = self.gathered
+        check(lib().gsb_merge_batch_device(self.device_index, stream.cuda_stream, src.data_ptr(), self.world, nq, k,
+                                           self.out_rows.data_ptr(), self.out_scores.data_ptr(),
+                                           self.out_n.data_ptr(), self.out_approx.data_ptr()))

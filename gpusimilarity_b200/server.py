@@ -96,6 +96,20 @@ class GPUSimServer:
         finally:
             lib().gsb_server_free(resp)
 
+    def handleBatch(self, requests: Sequence[bytes]) -> List[bytes]:
+        """Requests of the same shape answered from one pass over each database."""
+        n = len(requests)
+        bufs = [C.create_string_buffer(r, len(r)) for r in requests]
+        ptrs = (C.c_void_p * n)(*[C.cast(b, C.c_void_p) for b in bufs])
+        sizes = (C.c_uint64 * n)(*[len(r) for r in requests])
+        out, out_n = (C.c_void_p * n)(), (C.c_uint64 * n)()
+        _check(lib().gsb_server_handle_batch(self._h, ptrs, sizes, n, out, out_n))
+        res = []
+        for i in range(n):
+            res.append(C.string_at(out[i], out_n[i]))
+            lib().gsb_server_free(out[i])
+        return res
+
     def searchDatabases(self, reference, results_requested: int, similarity_cutoff: float,
                         dbname_to_key: Dict[str, str]):
         """reference searchDatabases (gpusim.cpp:306-374): (smiles, ids, scores, approximate count)."""

@@ -91,7 +91,9 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
                   uint64_t* out_approx);
 /* New (the reference serves one query per request, gpusim.cpp:407-414): n_queries queries
  * over the same database; query q's results land at out_rows + q*k etc.  Identical results to
- * n_queries calls of gsb_db_search. */
+ * n_queries calls of gsb_db_search.  With the default layout, rows of at most 1024 bits, no fold
+ * and k <= 512 the queries share ONE pass over the database per group of 256 (multi-query
+ * kernel, POPC-bound instead of HBM-bound); otherwise they are searched one after the other. */
 int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words,
                         int n_queries, uint32_t k, float cutoff, uint32_t* out_rows,
                         float* out_scores, uint32_t* out_n, uint64_t* out_approx);
@@ -120,6 +122,19 @@ int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query,
 int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint32_t* d_counts,
                      int n_lists, uint32_t list_stride, uint32_t k, uint32_t* d_out_rows,
                      float* d_out_scores, uint32_t* d_out_n);
+
+/* Multi-query scan of this process's shard: n_queries (1..256) queries in device memory
+ * ([n_queries][fp_bits/32] words) are scored against every row in ONE pass over the database.
+ * d_out_keys [n_queries][k] (best first, zero padded), d_out_n [n_queries], d_out_survivors
+ * [n_queries].  Needs the default layout, fingerprints of at most 1024 bits and k <= 512. */
+int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_queries, int n_queries,
+                               uint32_t k, float cutoff, gsb_key* d_out_keys, uint32_t* d_out_n,
+                               uint64_t* d_out_survivors);
+/* Merge of all-gathered per-rank batch records (per rank: [n_queries][k] keys, [n_queries]
+ * survivors, [n_queries] counts, u64 each): one CTA per query. */
+int gsb_merge_batch_device(int device, void* stream, const gsb_key* d_records, int n_ranks, int n_queries,
+                           uint32_t k, uint32_t* d_out_rows, float* d_out_scores, uint32_t* d_out_n,
+                           uint64_t* d_out_approx);
 
 /* Fused scan + cross-GPU exchange + merge in ONE launch per rank: the last CTA of every rank's
  * scan stores its shard's candidate record straight into every rank's exchange buffer through
@@ -179,6 +194,11 @@ int gsb_server_get_fingerprint(const gsb_server* srv, const char* dbname, uint64
 int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t request_bytes,
                               void** response, uint64_t* response_bytes);
 void gsb_server_free(void* p);
+/* New: n requests that ask the same thing (databases + keys, result count, cutoff, query width)
+ * answered from ONE pass over each database (gsb_db_search_batch).  The event loop does this by
+ * itself for requests that arrive together.  responses[i] is malloc'ed: gsb_server_free. */
+int gsb_server_handle_batch(gsb_server* srv, const void* const* requests, const uint64_t* request_bytes,
+                            int n, void** responses, uint64_t* response_bytes);
 /* setupSocket (gpusim.cpp:255-274): unix socket, default "/tmp/gpusimilarity" (what QLocalServer
  * name "gpusimilarity" resolves to); then the one-request-at-a-time event loop. */
 int gsb_server_listen(gsb_server* srv, const char* socket_path);

@@ -294,6 +294,36 @@ def test_partition_invariance_200m_rows():
     assert np.array_equal(cr[order], rows) and np.array_equal(f32bits(cs[order]), f32bits(scores))
 
 
+@pytest.mark.parametrize("bits,n_queries,k", [(1024, 37, 100), (1024, 300, 100), (256, 64, 10), (1024, 5, 512)])
+def test_multi_query_kernel(bits, n_queries, k):
+    """BASELINE config 5 in small: gsb_db_search_batch (one pass over the database for up to 256
+    queries) must equal n_queries independent searches, i.e. the oracle per query."""
+    words = bits // 32
+    rows_np = OC.c_synth_db(bits + n_queries, 200_000, words, 97)
+    rows_np[1000:1100] = rows_np[5]                                 # a tie group
+    rows_np[2000:2050] = 0                                          # empty fingerprints
+    db = make_db(rows_np)
+    rng = np.random.default_rng(n_queries)
+    qs = np.stack([O.synth_template(bits + n_queries, words), np.zeros(words, np.int32), rows_np[5]] +
+                  [rows_np[i] for i in rng.integers(0, 200_000, n_queries - 3)])
+    for cutoff in (0.0, 0.15):
+        res = db.search_batch_rows(qs, k, cutoff)
+        assert len(res) == n_queries
+        for j, got in enumerate(res):
+            assert_same(got, OC.c_search(qs[j], rows_np, k, cutoff), f"batch query {j} cutoff {cutoff}")
+
+
+def test_multi_query_matches_single_query_path(monkeypatch):
+    rows_np = OC.c_synth_db(4, 500_000, 32, 211)
+    db = make_db(rows_np)
+    qs = np.stack([rows_np[i * 1000] for i in range(20)])
+    batched = db.search_batch_rows(qs, 100, 0.0)
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "0")
+    looped = db.search_batch_rows(qs, 100, 0.0)
+    for a, b in zip(batched, looped):
+        assert_same(a, b, "batch kernel vs loop")
+
+
 def test_device_entry_points_and_merge_kernel():
     """The one-process-per-GPU path on one GPU: three shards with row bases, searched through
     gsb_db_search_device on a torch stream, merged by gsb_merge_device."""
@@ -326,6 +356,47 @@ def test_device_entry_points_and_merge_kernel():
         cnt = int(out_n.item())
         got = (out_rows[:cnt].cpu().numpy().astype(np.int64) & 0xffffffff, out_scores[:cnt].cpu().numpy(), approx)
         assert_same(got, OC.c_search(q_np, whole_np, k, cutoff), f"3 shards cutoff={cutoff}")
+
+
+def test_sharded_multi_query_merge():
+    """Config 5 plumbing on one GPU: three shards searched with the multi-query kernel, records
+    concatenated as an all-gather would, merged by gsb_merge_batch_device (one CTA per query)."""
+    import torch
+    from gpusimilarity_b200.dist import ShardedBatchSearcher, shard_range
+    from gpusimilarity_b200._lib import check, lib
+    n, k, seed, plant, nq, world = 450_000, 100, 55, 300, 24, 3
+    whole_np = OC.c_synth_db(seed, n, 32, plant)
+    qs = np.stack([O.synth_template(seed, 32)] + [whole_np[i * 997] for i in range(nq - 1)])
+    dev = torch.device("cuda", 0)
+    d_q = torch.from_numpy(qs.copy()).to(dev)
+    stream = torch.cuda.current_stream()
+    for cutoff in (0.0, 0.25):
+        recs = []
+        for r in range(world):
+            base, rows = shard_range(n, r, world)
+            shard = gsb.FingerprintDB.synthetic(rows, device=0, seed=seed, plant_period=plant, row_base=base)
+            s = ShardedBatchSearcher(shard, k, 0)
+            p = s.rec.data_ptr()
+            check(lib().gsb_db_search_batch_device(shard._h, stream.cuda_stream, d_q.data_ptr(), nq, k, cutoff, p,
+                                                   p + 8 * nq * (k + 1), p + 8 * nq * k))
+            torch.cuda.synchronize()
+            recs.append(s.rec[:nq * (k + 2)].clone())
+            shard.close()
+        gathered = torch.cat(recs)
+        merger = ShardedBatchSearcher.__new__(ShardedBatchSearcher)
+        out_rows = torch.zeros(nq * k, dtype=torch.int32, device=dev)
+        out_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
+        out_n = torch.zeros(nq, dtype=torch.int32, device=dev)
+        out_approx = torch.zeros(nq, dtype=torch.int64, device=dev)
+        check(lib().gsb_merge_batch_device(0, stream.cuda_stream, gathered.data_ptr(), world, nq, k, out_rows.data_ptr(),
+                                           out_scores.data_ptr(), out_n.data_ptr(), out_approx.data_ptr()))
+        torch.cuda.synchronize()
+        rows_h = out_rows.cpu().numpy().astype(np.int64).reshape(nq, k) & 0xffffffff
+        scores_h = out_scores.cpu().numpy().reshape(nq, k)
+        for j in range(nq):
+            c = int(out_n[j].item())
+            assert_same((rows_h[j, :c], scores_h[j, :c], int(out_approx[j].item())),
+                        OC.c_search(qs[j], whole_np, k, cutoff), f"sharded batch query {j}")
 
 
 def test_fused_peer_exchange_two_ranks_on_one_gpu(monkeypatch):

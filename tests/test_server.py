@@ -127,6 +127,36 @@ def test_search_multiple_gpu(two_dbs, small_db, golden):
 
 
 @pytest.mark.gpu
+def test_batched_requests_equal_single_requests(two_dbs, small_db, tmp_path):
+    """Daemon-side batching: requests of one shape go through gsb_db_search_batch (one pass over
+    each database) and must produce byte-identical responses; also through the socket loop with
+    clients that send at the same time."""
+    server = GPUSimServer(list(two_dbs))
+    names = {"small": "pass", "small_copy": "pass"}
+    reqs = [encode_request(names, 500 + i, 8, 0.05, small_db[row]) for i, row in enumerate((0, 3, 17, 42, 99, 3))]
+    single = [server.handleRequest(r) for r in reqs]
+    assert server.handleBatch(reqs) == single
+    with pytest.raises(gsb.GsbError):
+        server.handleBatch([reqs[0], encode_request(names, 1, 9, 0.05, small_db[0])])
+    path = str(tmp_path / "batch.sock")
+    server.listen(path)
+    th = threading.Thread(target=server.serve, args=(len(reqs),), daemon=True)
+    th.start()
+    out = [None] * len(reqs)
+
+    def client(i):
+        out[i] = search_over_socket(reqs[i], path)
+
+    clients = [threading.Thread(target=client, args=(i,)) for i in range(len(reqs))]
+    for c in clients:
+        c.start()
+    for c in clients:
+        c.join(timeout=30)
+    th.join(timeout=10)
+    assert out == single
+
+
+@pytest.mark.gpu
 def test_folded_server(two_dbs, small_db):
     server = GPUSimServer([two_dbs[0]], gpu_bitcount=512)
     assert server.foldFactor() == 2
