@@ -453,6 +453,27 @@ def test_fused_peer_exchange_two_ranks_on_one_gpu(monkeypatch):
             assert_same(got, want, f"fused rank {r} seq {seq}")
 
 
+@pytest.mark.skipif(gsb.get_gpu_count() < 2, reason="needs two GPUs in one process")
+def test_single_process_multi_device_shards():
+    """The reference's own multi-GPU mode: one process, chunks spread over the visible devices
+    (fingerprintdb_cuda.cu:176-183), per-device results merged on the host (:366)."""
+    n = 2_000_001
+    rows_np = OC.c_synth_db(71, n, 32, 900)
+    devices = list(range(min(gsb.get_gpu_count(), 4)))
+    db = make_db(rows_np, devices=devices)
+    assert db.shardCount() == len(devices)
+    qs = [O.synth_template(71, 32), rows_np[0], rows_np[n - 1]]
+    for q in qs:
+        for k, cutoff in ((10, 0.0), (1000, 0.0), (1000, 0.2), (20000, 0.0)):
+            check(db, rows_np, q, k, cutoff, f"{len(devices)} devices")
+    res = db.search_batch_rows(np.stack(qs), 100, 0.1)
+    for q, got in zip(qs, res):
+        assert_same(got, OC.c_search(q, rows_np, 100, 0.1), "multi-device batch")
+    db2 = make_db(rows_np, fold=2, devices=devices)
+    rows, scores, approx = db2.search_rows(qs[0], 10, 0.3)
+    assert np.all(scores >= np.float32(0.3)) and np.all(np.diff(scores) <= 0)
+
+
 def test_errors_are_loud():
     rows_np = O.synth_db(1, 1000, 32, 0)
     db = gsb.FingerprintDB(1024, 1000, "pass", [rows_np])
