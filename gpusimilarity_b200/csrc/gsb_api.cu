@@ -92,6 +92,8 @@ int make_layout(uint32_t words, Layout* out)
 struct Workspace {
     cudaStream_t stream = nullptr;
     gsb::ScanCtrl* ctrl = nullptr;
+    unsigned int* ghist = nullptr;
+    unsigned long long* gfinal = nullptr;
     unsigned long long* cta_keys = nullptr;
     uint32_t* cta_counts = nullptr;
     uint64_t cta_keys_cap = 0; // entries
@@ -166,9 +168,11 @@ template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
         configured[dev] = plan.smem;
     }
-    gsb::scan_topk_kernel<W, RP, CW, U><<<plan.grid, CW * 32, plan.smem, st>>>(p);
+    // cooperative launch: every CTA must be resident, the kernel lines them up on an arrival counter
+    void* args[] = {const_cast<gsb::ScanParams*>(&p)};
+    GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_topk_kernel<W, RP, CW, U>), dim3(plan.grid),
+                                         dim3(CW * 32), args, plan.smem, st));
     g_launches++;
-    GSB_CUDA(cudaGetLastError());
     return GSB_OK;
 }
 
@@ -260,9 +264,12 @@ int ws_init(Shard& sh)
     GSB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     GSB_CUDA(cudaMalloc(&ws.ctrl, sizeof(gsb::ScanCtrl)));
     GSB_CUDA(cudaMemset(ws.ctrl, 0, sizeof(gsb::ScanCtrl)));
+    GSB_CUDA(cudaMalloc(&ws.ghist, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMemset(ws.ghist, 0, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMalloc(&ws.gfinal, 32768 * 8));
     int sms = 0;
     GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
-    ws.max_grid = sms * std::max(1, env_int("GSB_CTAS_PER_SM", 1));
+    ws.max_grid = sms; // persistent: one CTA per SM (shared memory allows no more), all resident
     GSB_CUDA(cudaMalloc(&ws.cta_counts, sizeof(uint32_t) * 4096));
     return GSB_OK;
 }
@@ -300,6 +307,8 @@ void ws_free(Shard& sh)
     if (ws.stream)
         cudaStreamDestroy(ws.stream);
     cudaFree(ws.ctrl);
+    cudaFree(ws.ghist);
+    cudaFree(ws.gfinal);
     cudaFree(ws.cta_keys);
     cudaFree(ws.cta_counts);
     cudaFree(ws.out_dev);
@@ -430,6 +439,8 @@ void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k
     p->cta_keys = sh.ws.cta_keys;
     p->cta_counts = sh.ws.cta_counts;
     p->ctrl = sh.ws.ctrl;
+    p->ghist = sh.ws.ghist;
+    p->gfinal = sh.ws.gfinal;
 }
 
 struct Cand {
