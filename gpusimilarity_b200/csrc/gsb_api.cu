@@ -497,8 +497,8 @@ int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, f
             unsigned long long t0 = ~0ull;
             for (int c = 0; c < plans[i].grid; c++)
                 t0 = std::min(t0, h[c * 8]);
-            const char* names[7] = {"start", "first data", "warp0 out of work", "cta out of work", "final select",
-                                    "ticket", "merge done"};
+            const char* names[7] = {"start", "(unused)", "warp0 out of work", "cta out of work", "global histogram read",
+                                    "ticket", "final sort done"};
             for (int s = 0; s < 7; s++) {
                 unsigned long long lo = ~0ull, hi = 0;
                 double sum = 0;
