@@ -897,6 +897,8 @@ int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, in
         return fail(GSB_ERR_INVALID, "null argument");
     if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
         return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
+    if (fp_count > 0xfffffffeull) // results carry 32-bit row ids (the .fsim format caps N at 2^31-1)
+        return fail(GSB_ERR_INVALID, "more than 2^32-2 rows");
     const uint64_t row_bytes = fp_bits / 8;
     uint64_t total = 0;
     for (int c = 0; c < n_chunks; c++) {
@@ -1200,6 +1202,7 @@ int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query,
         return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
     if (db->fold_factor != 1)
         return fail(GSB_ERR_STATE, "device search does not re-score folded databases");
+    std::lock_guard<std::mutex> lock(db->mu); // launch planning and workspace growth are not re-entrant
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     Plan plan;
     int rc = make_plan(db->layout, sh, k, &plan);
@@ -1230,6 +1233,7 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
     if (!db->layout.rowpop || db->layout.dev_words > 32 || db->layout.dev_words != db->words || db->fold_factor != 1 ||
         k < 1 || k > gsb::kMaxBatchK)
         return fail(GSB_ERR_INVALID, "the multi-query kernel needs the default layout, <= 1024 bits, k <= 512");
+    std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_queries),
                               static_cast<uint32_t>(n_queries), k, cutoff,
@@ -1276,6 +1280,7 @@ int gsb_db_search_device_fused(const gsb_db* db, void* stream, const int32_t* d_
         return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
     if (db->fold_factor != 1)
         return fail(GSB_ERR_STATE, "device search does not re-score folded databases");
+    std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     Plan plan;
     int rc = make_plan(db->layout, sh, k, &plan);

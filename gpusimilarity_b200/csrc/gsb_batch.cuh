@@ -286,7 +286,10 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     // ---- grid-wide arrival (the grid is persistent: one CTA per SM, all resident)
     if (tid == 0) {
         atomicAdd(&p.ctrl->ticket, 1u);
+        const long long t0 = clock64();
         while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < gridDim.x) {
+            if (clock64() - t0 > (200ll << 30)) // ~100 s (CTAs finish far apart here); fail loudly, never hang
+                __trap();
         }
         __threadfence();
     }

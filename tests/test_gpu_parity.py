@@ -474,6 +474,50 @@ def test_single_process_multi_device_shards():
     assert np.all(scores >= np.float32(0.3)) and np.all(np.diff(scores) <= 0)
 
 
+def test_degenerate_inputs():
+    rows_np = O.synth_db(2, 3000, 32, 0)
+    db = make_db(rows_np)
+    rows, scores, approx = db.search_rows(rows_np[1], 0, 0.0)             # k = 0: nothing, count still right
+    assert len(rows) == 0 and approx == 3000
+    rows, scores, approx = db.search_rows(rows_np[1], 0, 0.2)
+    assert len(rows) == 0 and approx == OC.c_search(rows_np[1], rows_np, 1, 0.2)[2]
+    empty = gsb.FingerprintDB(1024, 0, "pass", [])
+    empty.copyToGPU(1)
+    rows, scores, approx = empty.search_rows(rows_np[1], 10, 0.0)
+    assert len(rows) == 0 and approx == 0
+    one = make_db(rows_np[:1])
+    check(one, rows_np[:1], rows_np[0], 5, 0.0, "one row")
+    ones = np.full((200, 32), -1, dtype=np.int32)                         # every bit set: union 1024
+    full = make_db(ones)
+    check(full, ones, ones[0], 10, 0.0, "all ones")
+    check(full, ones, rows_np[0], 10, 0.0, "all ones db, sparse query")
+
+
+def test_concurrent_searches_from_threads():
+    """One search in flight per database (like the reference), but callers may come from several
+    threads and several databases may be searched at the same time."""
+    import threading
+    a_np, b_np = O.synth_db(8, 120000, 32, 31), O.synth_db(9, 90000, 32, 17)
+    dbs = [(make_db(a_np), a_np, O.synth_template(8, 32)), (make_db(b_np), b_np, O.synth_template(9, 32))]
+    want = {i: OC.c_search(q, rows, 500, 0.0) for i, (_, rows, q) in enumerate(dbs)}
+    errors = []
+
+    def worker(i):
+        try:
+            db, rows, q = dbs[i % 2]
+            for _ in range(10):
+                assert_same(db.search_rows(q, 500, 0.0), want[i % 2], f"thread {i}")
+        except Exception as e:  # noqa: BLE001
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+
+
 def test_errors_are_loud():
     rows_np = O.synth_db(1, 1000, 32, 0)
     db = gsb.FingerprintDB(1024, 1000, "pass", [rows_np])
