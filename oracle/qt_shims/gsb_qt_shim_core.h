@@ -6,6 +6,8 @@
 #pragma once
 #include <algorithm>
 #include <climits>
+#include <condition_variable>
+#include <memory>
 #include <cmath>
 #include <cstdlib>
 #include <functional>
@@ -102,13 +104,64 @@ class QThreadPool
 
 namespace QtConcurrent
 {
-// QtConcurrent::run(obj, &Class::method, args...) -> runs on another thread (Qt: global pool).
+// The global thread pool Qt hands QtConcurrent::run jobs to: persistent workers (one per logical
+// core, like QThreadPool::globalInstance()), so that per-thread CUDA state is set up once and not
+// on every query as it would be with a fresh std::thread per job.
+class GsbShimPool
+{
+  public:
+    static GsbShimPool& instance()
+    {
+        // leaked on purpose: the workers block on the condition variable for the life of the
+        // process, and destroying a condition variable with waiters at exit would hang
+        static GsbShimPool* pool = new GsbShimPool;
+        return *pool;
+    }
+    std::shared_future<void> submit(std::function<void()> fn)
+    {
+        auto task = std::make_shared<std::packaged_task<void()>>(std::move(fn));
+        std::shared_future<void> fut = task->get_future().share();
+        {
+            std::lock_guard<std::mutex> lock(m_mu);
+            m_jobs.push_back([task]() { (*task)(); });
+        }
+        m_cv.notify_one();
+        return fut;
+    }
+
+  private:
+    GsbShimPool()
+    {
+        unsigned n = std::thread::hardware_concurrency();
+        if (n < 1)
+            n = 1;
+        for (unsigned i = 0; i < n; i++)
+            std::thread([this]() { work(); }).detach();
+    }
+    void work()
+    {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lock(m_mu);
+                m_cv.wait(lock, [this]() { return !m_jobs.empty(); });
+                job = std::move(m_jobs.front());
+                m_jobs.erase(m_jobs.begin());
+            }
+            job();
+        }
+    }
+    std::mutex m_mu;
+    std::condition_variable m_cv;
+    std::vector<std::function<void()>> m_jobs;
+};
+
+// QtConcurrent::run(obj, &Class::method, args...) -> runs on the global pool.
 template <typename C, typename M, typename... A>
 QFuture<void> run(C* obj, M method, A... args)
 {
-    auto fut = std::async(std::launch::async,
-                          [obj, method, args...]() { (obj->*method)(args...); });
-    return QFuture<void>(fut.share());
+    return QFuture<void>(
+        GsbShimPool::instance().submit([obj, method, args...]() { (obj->*method)(args...); }));
 }
 
 // QtConcurrent::blockingMap(sequence, functor): apply functor to every element in place using
