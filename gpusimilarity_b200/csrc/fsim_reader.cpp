@@ -9,6 +9,7 @@
 // qCompress = u32 BE uncompressed length + zlib stream.  Chunks are inflated in parallel (the
 // reference uses a QThreadPool, gpusim.cpp:202-236).
 #include "../../include/gpusim_b200.h"
+#include "gsb_internal.h"
 
 #include <zlib.h>
 
@@ -203,15 +204,15 @@ const char* gsb_fsim_string(const gsb_fsim* f, int which, uint64_t index)
     return index < v.size() ? v[index] : nullptr;
 }
 
-int gsb_fsim_create_db(const gsb_fsim* f, gsb_db** out)
+int gsb_fsim_create_db(gsb_fsim* f, gsb_db** out)
 {
-    std::vector<const void*> ptrs;
-    std::vector<uint64_t> sizes;
-    for (const Blob& b : f->fp) {
-        ptrs.push_back(b.raw.data());
-        sizes.push_back(b.raw.size());
-    }
-    return gsb_db_create(ptrs.data(), sizes.data(), static_cast<int>(ptrs.size()), f->fp_bits, f->fp_count, out);
+    // the database adopts the inflated fingerprint chunks (no second copy of a 100 GB database in
+    // host memory); the file object keeps the SMILES / id strings
+    std::vector<std::vector<uint8_t>> chunks;
+    for (Blob& b : f->fp)
+        chunks.push_back(std::move(b.raw));
+    f->fp.clear();
+    return gsb_db_create_adopt(std::move(chunks), f->fp_bits, f->fp_count, out);
 }
 
 } // extern "C"

@@ -9,6 +9,7 @@
 #include "gsb_kernels.cuh"
 
 #include "../../include/gpusim_b200.h"
+#include "gsb_internal.h"
 
 #include <algorithm>
 #include <atomic>
@@ -138,7 +139,25 @@ struct gsb_db {
     int fp_bits = 0;
     uint32_t words = 0; // unfolded words per row
     uint64_t count = 0;
-    std::vector<uint32_t> host; // unfolded rows, row-major (empty for device-generated shards)
+    // unfolded rows on the host, chunk by chunk as they arrived (empty for device-generated
+    // shards): used by the upload, getFingerprint, search_cpu and the fold re-score
+    struct HostChunk {
+        std::vector<uint8_t> bytes;
+        uint64_t row0 = 0, n_rows = 0;
+    };
+    std::vector<HostChunk> host;
+    const uint32_t* host_row(uint64_t row) const
+    {
+        size_t lo = 0, hi = host.size();
+        while (hi - lo > 1) {
+            const size_t mid = (lo + hi) / 2;
+            if (host[mid].row0 <= row)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        return reinterpret_cast<const uint32_t*>(host[lo].bytes.data()) + (row - host[lo].row0) * words;
+    }
     unsigned fold_factor = 1;
     Layout layout;
     std::vector<Shard> shards;
@@ -233,7 +252,7 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
     for (int warps = pref; warps >= 4; warps -= 4) {
         int grid = sh.ws.max_grid;
         if (const int g = env_int("GSB_GRID", 0))
-            grid = std::min(g, 4096);
+            grid = std::min(g, grid); // never more CTAs than can be resident together
         const uint32_t n_super = (sh.n_tiles + warps - 1) / warps;
         grid = std::max(1, std::min<int>(grid, n_super ? n_super : 1));
         const uint32_t threads = warps * 32;
@@ -383,38 +402,51 @@ int upload_rows(const gsb_db* db, Shard& sh)
     const uint32_t f = db->fold_factor;
     const uint64_t src_row_bytes = static_cast<uint64_t>(src_words) * 4;
     const uint64_t piece_rows = std::max<uint64_t>(32, ((64ull << 20) / src_row_bytes) / 32 * 32);
-    uint8_t* pinned[2] = {nullptr, nullptr};
-    uint8_t* staged[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
+    struct Staging { // released on every exit path
+        uint8_t* pinned[2] = {nullptr, nullptr};
+        uint8_t* staged[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        ~Staging()
+        {
+            for (int i = 0; i < 2; i++) {
+                if (pinned[i])
+                    cudaFreeHost(pinned[i]);
+                cudaFree(staged[i]);
+                if (done[i])
+                    cudaEventDestroy(done[i]);
+            }
+        }
+    } stg;
+    uint8_t** pinned = stg.pinned;
+    uint8_t** staged = stg.staged;
+    cudaEvent_t* done = stg.done;
     for (int i = 0; i < 2; i++) {
         GSB_CUDA(cudaMallocHost(&pinned[i], piece_rows * src_row_bytes));
         GSB_CUDA(cudaMalloc(&staged[i], piece_rows * src_row_bytes));
         GSB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     }
-    const uint8_t* base = reinterpret_cast<const uint8_t*>(db->host.data() + sh.row_base * src_words);
     int slot = 0;
-    for (uint64_t r0 = 0; r0 < sh.n_rows; r0 += piece_rows, slot ^= 1) {
-        const uint64_t rows = std::min<uint64_t>(piece_rows, sh.n_rows - r0);
-        GSB_CUDA(cudaEventSynchronize(done[slot])); // the previous use of this slot has been consumed
-        const uint8_t* src = base + r0 * src_row_bytes;
-        uint8_t* dst = pinned[slot];
-        parallel_for(rows, [=](uint64_t lo, uint64_t hi) {
-            std::memcpy(dst + lo * src_row_bytes, src + lo * src_row_bytes, (hi - lo) * src_row_bytes);
-        });
-        GSB_CUDA(cudaMemcpyAsync(staged[slot], pinned[slot], rows * src_row_bytes, cudaMemcpyHostToDevice,
-                                 sh.ws.stream));
-        const uint64_t threads = rows * l.dev_words;
-        gsb::ingest_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, sh.ws.stream>>>(
-            reinterpret_cast<const uint32_t*>(staged[slot]), rows, r0, src_words, f, sh.tiles, l.tile_stride,
-            l.dev_words, l.rowpop ? 1 : 0);
-        g_launches++;
-        GSB_CUDA(cudaEventRecord(done[slot], sh.ws.stream));
-    }
-    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
-    for (int i = 0; i < 2; i++) {
-        cudaFreeHost(pinned[i]);
-        cudaFree(staged[i]);
-        cudaEventDestroy(done[i]);
+    for (const gsb_db::HostChunk& hc : db->host) {
+        // rows of this host chunk that belong to the shard
+        const uint64_t lo_row = std::max<uint64_t>(hc.row0, sh.row_base);
+        const uint64_t hi_row = std::min<uint64_t>(hc.row0 + hc.n_rows, sh.row_base + sh.n_rows);
+        for (uint64_t g0 = lo_row; g0 < hi_row; g0 += piece_rows, slot ^= 1) {
+            const uint64_t rows = std::min<uint64_t>(piece_rows, hi_row - g0);
+            GSB_CUDA(cudaEventSynchronize(done[slot])); // the previous use of this slot has been consumed
+            const uint8_t* src = hc.bytes.data() + (g0 - hc.row0) * src_row_bytes;
+            uint8_t* dst = pinned[slot];
+            parallel_for(rows, [=](uint64_t lo, uint64_t hi) {
+                std::memcpy(dst + lo * src_row_bytes, src + lo * src_row_bytes, (hi - lo) * src_row_bytes);
+            });
+            GSB_CUDA(cudaMemcpyAsync(staged[slot], pinned[slot], rows * src_row_bytes, cudaMemcpyHostToDevice,
+                                     sh.ws.stream));
+            const uint64_t threads = rows * l.dev_words;
+            gsb::ingest_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, sh.ws.stream>>>(
+                reinterpret_cast<const uint32_t*>(staged[slot]), rows, g0 - sh.row_base, src_words, f, sh.tiles,
+                l.tile_stride, l.dev_words, l.rowpop ? 1 : 0);
+            g_launches++;
+            GSB_CUDA(cudaEventRecord(done[slot], sh.ws.stream));
+        }
     }
     GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
     GSB_CUDA(cudaGetLastError());
@@ -838,6 +870,42 @@ int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<
 
 } // namespace
 
+int gsb_db_create_adopt(std::vector<std::vector<uint8_t>>&& chunks, int fp_bits, uint64_t fp_count, gsb_db** out)
+{
+    if (!out)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
+        return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
+    if (fp_count > 0xfffffffeull) // results carry 32-bit row ids (the .fsim format caps N at 2^31-1)
+        return fail(GSB_ERR_INVALID, "more than 2^32-2 rows");
+    const uint64_t row_bytes = fp_bits / 8;
+    uint64_t total = 0;
+    for (const auto& c : chunks) {
+        if (c.size() % row_bytes != 0)
+            return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
+        total += c.size() / row_bytes;
+    }
+    if (total != fp_count) // reference fingerprintdb_cuda.cu:153-156
+        return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
+    std::unique_ptr<gsb_db> db(new gsb_db);
+    db->fp_bits = fp_bits;
+    db->words = fp_bits / 32;
+    db->count = fp_count;
+    uint64_t row0 = 0;
+    for (auto& c : chunks) {
+        if (c.empty())
+            continue;
+        gsb_db::HostChunk hc;
+        hc.n_rows = c.size() / row_bytes;
+        hc.row0 = row0;
+        hc.bytes = std::move(c);
+        row0 += hc.n_rows;
+        db->host.push_back(std::move(hc));
+    }
+    *out = db.release();
+    return GSB_OK;
+}
+
 // ====================================================================================== C ABI
 extern "C" {
 
@@ -897,31 +965,12 @@ int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, in
 {
     if (!out || n_chunks < 0 || (n_chunks > 0 && (!chunk_ptrs || !chunk_bytes)))
         return fail(GSB_ERR_INVALID, "null argument");
-    if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
-        return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
-    if (fp_count > 0xfffffffeull) // results carry 32-bit row ids (the .fsim format caps N at 2^31-1)
-        return fail(GSB_ERR_INVALID, "more than 2^32-2 rows");
-    const uint64_t row_bytes = fp_bits / 8;
-    uint64_t total = 0;
-    for (int c = 0; c < n_chunks; c++) {
-        if (chunk_bytes[c] % row_bytes != 0)
-            return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
-        total += chunk_bytes[c] / row_bytes;
+    std::vector<std::vector<uint8_t>> chunks(n_chunks);
+    for (int c = 0; c < n_chunks; c++) { // the reference copies the chunk bytes too (.cu:123-125)
+        const uint8_t* p = static_cast<const uint8_t*>(chunk_ptrs[c]);
+        chunks[c].assign(p, p + chunk_bytes[c]);
     }
-    if (total != fp_count) // reference fingerprintdb_cuda.cu:153-156
-        return fail(GSB_ERR_CORRUPT, "Mismatch between FP count and data, potential database corruption.");
-    std::unique_ptr<gsb_db> db(new gsb_db);
-    db->fp_bits = fp_bits;
-    db->words = fp_bits / 32;
-    db->count = fp_count;
-    db->host.resize(fp_count * db->words);
-    uint64_t off = 0;
-    for (int c = 0; c < n_chunks; c++) {
-        std::memcpy(reinterpret_cast<uint8_t*>(db->host.data()) + off, chunk_ptrs[c], chunk_bytes[c]);
-        off += chunk_bytes[c];
-    }
-    *out = db.release();
-    return GSB_OK;
+    return gsb_db_create_adopt(std::move(chunks), fp_bits, fp_count, out);
 }
 
 int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base, uint64_t seed,
@@ -1063,7 +1112,7 @@ int gsb_db_get_fingerprint(const gsb_db* db, uint64_t row, int32_t* out_words)
     if (row >= db->count)
         return fail(GSB_ERR_INVALID, "row out of range");
     if (!db->host.empty()) {
-        std::memcpy(out_words, db->host.data() + row * db->words, db->words * 4);
+        std::memcpy(out_words, db->host_row(row), db->words * 4);
         return GSB_OK;
     }
     std::vector<uint32_t> tmp;
@@ -1118,10 +1167,12 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
     const uint32_t* qfull = reinterpret_cast<const uint32_t*>(query_words);
     for (size_t i = 0; i < keys.size(); i++) {
         cand[i].row = decode(keys[i]).row;
-        cand[i].score = score_cpu(qfull, db->host.data() + static_cast<uint64_t>(cand[i].row) * db->words, db->words);
+        cand[i].score = score_cpu(qfull, db->host_row(cand[i].row), db->words);
     }
     // top_results_bubble_sort (.cpp:92-103) == stable descending sort of the candidate order
-    std::stable_sort(cand.begin(), cand.end(), [](const Cand& a, const Cand& b) { return a.score > b.score; });
+    auto nan_last = [](float s) { return s != s ? -1.0f : s; };
+    std::stable_sort(cand.begin(), cand.end(),
+                     [&](const Cand& a, const Cand& b) { return nan_last(a.score) > nan_last(b.score); });
     uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cand.size(), k));
     for (uint32_t i = 0; i < n; i++) {
         if (cand[i].score < cutoff) { // .cu:323-326
@@ -1168,12 +1219,15 @@ int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words,
     const uint32_t* q = reinterpret_cast<const uint32_t*>(query_words);
     std::vector<float> scores(db->count);
     const uint32_t words = db->words;
-    const uint32_t* rows = db->host.data();
     float* sp = scores.data();
-    parallel_for(db->count, [=](uint64_t lo, uint64_t hi) {
-        for (uint64_t r = lo; r < hi; r++)
-            sp[r] = score_cpu(q, rows + r * words, words);
-    });
+    for (const gsb_db::HostChunk& hc : db->host) { // every chunk (the reference only looks at the first)
+        const uint32_t* rows = reinterpret_cast<const uint32_t*>(hc.bytes.data());
+        float* out = sp + hc.row0;
+        parallel_for(hc.n_rows, [=](uint64_t lo, uint64_t hi) {
+            for (uint64_t r = lo; r < hi; r++)
+                out[r] = score_cpu(q, rows + r * words, words);
+        });
+    }
     const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(k, db->count));
     std::vector<uint32_t> idx(db->count);
     for (uint64_t i = 0; i < db->count; i++)

@@ -169,8 +169,9 @@ const void* gsb_fsim_chunk_data(const gsb_fsim* f, int chunk);
 uint64_t gsb_fsim_chunk_bytes(const gsb_fsim* f, int chunk);
 uint64_t gsb_fsim_string_count(const gsb_fsim* f, int which);          /* which: 0 SMILES, 1 ids */
 const char* gsb_fsim_string(const gsb_fsim* f, int which, uint64_t index);
-/* gsb_db_create over the file's fingerprint chunks. */
-int gsb_fsim_create_db(const gsb_fsim* f, gsb_db** out);
+/* gsb_db_create over the file's fingerprint chunks WITHOUT copying them: the database adopts the
+ * inflated buffers (afterwards gsb_fsim_chunk_count() is 0; the strings stay with the file). */
+int gsb_fsim_create_db(gsb_fsim* f, gsb_db** out);
 
 /* ---- serving (reference GPUSimServer, gpusim.h:23-95 / gpusim.cpp:87-461), without Qt ----
  * Loads the .fsim files (database name = file base name, gpusim.cpp:114-116), applies the

@@ -474,6 +474,21 @@ def test_single_process_multi_device_shards():
     assert np.all(scores >= np.float32(0.3)) and np.all(np.diff(scores) <= 0)
 
 
+def test_multi_chunk_upload():
+    """Host chunks that do not line up with 32-row batches, pieces or shards."""
+    n = 700_003
+    rows_np = OC.c_synth_db(88, n, 32, 401)
+    cuts = [0, 5, 100_001, 100_002, 333_333, n]
+    db = gsb.FingerprintDB(1024, n, "pass", [rows_np[a:b] for a, b in zip(cuts[:-1], cuts[1:])])
+    db.copyToGPU(1)
+    for q in (O.synth_template(88, 32), rows_np[100_001], rows_np[n - 1]):
+        check(db, rows_np, q, 100, 0.0, "multi-chunk")
+    db.copyToGPU(4)                                                   # folded upload from the same chunks
+    rows, scores, approx = db.search_rows(O.synth_template(88, 32), 10, 0.3)
+    w = O.search_gpu_folded(O.synth_template(88, 32), rows_np, 10, 0.3, 4)
+    assert np.array_equal(rows, w[0]) and np.array_equal(f32bits(scores), f32bits(w[1])) and approx == w[2]
+
+
 def test_degenerate_inputs():
     rows_np = O.synth_db(2, 3000, 32, 0)
     db = make_db(rows_np)

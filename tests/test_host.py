@@ -98,3 +98,21 @@ def test_fsim_round_trip(tmp_path, small_fsim):
     write_fsim(path, rows, smiles, ids, version=2)
     with pytest.raises(FsimError):
         read_fsim(path)
+
+
+def test_multi_chunk_host_storage():
+    """Several fingerprint chunks (as a > 1 GiB .fsim has): rows at the chunk boundaries come back
+    right (the reference's getStorageAndLocalIndex is off by one there, fingerprintdb_cuda.cu:204)
+    and search_cpu covers every chunk (the reference only searches the first, cpp:38,44)."""
+    rows = O.synth_db(21, 1000, 32, 13)
+    cuts = [0, 1, 257, 600, 1000]
+    chunks = [rows[a:b] for a, b in zip(cuts[:-1], cuts[1:])]
+    db = gsb.FingerprintDB(1024, 1000, "k", chunks)
+    for r in (0, 1, 2, 256, 257, 258, 599, 600, 601, 999):
+        assert np.array_equal(db.getFingerprint(r), rows[r]), r
+    q = O.synth_template(21, 32)
+    got_rows, got_scores = db.search_cpu_rows(q, 50)
+    want_rows, want_scores = O.search_cpu(q, rows, 50)
+    assert list(got_rows) == list(want_rows) and list(f32bits(got_scores)) == list(f32bits(want_scores))
+    with pytest.raises(gsb.GsbError):
+        db.getFingerprint(1000)
