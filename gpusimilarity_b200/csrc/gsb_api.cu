@@ -69,7 +69,10 @@ struct Layout {
     uint32_t row_bytes = 0;
     uint32_t tile_bytes = 0;  // bytes per bulk copy
     uint32_t tile_stride = 0; // distance between batches
-    uint32_t stage_bytes = 0; // ring slot
+    uint32_t unit_batches = 1;      // batches per work unit / TMA copy of the single-query scan (~4 KB)
+    uint32_t unit_bytes = 0;        // unit_batches * tile_stride
+    uint32_t stage_bytes = 0;       // ring slot of the single-query scan (one unit)
+    uint32_t batch_stage_bytes = 0; // ring slot of the multi-query scan (one batch)
     bool rowpop = false;
 };
 
@@ -85,9 +88,19 @@ int make_layout(uint32_t words, Layout* out)
     l.rowpop = env_int("GSB_ROWPOP", 1) != 0;
     l.tile_bytes = l.tile_rows * l.row_bytes + (l.rowpop ? l.tile_rows * 2 : 0);
     l.tile_stride = l.tile_bytes; // multiple of 16
-    l.stage_bytes = (l.tile_bytes + 127) / 128 * 128;
+    l.unit_batches = l.dev_words >= 32 ? 1 : 32 / l.dev_words;
+    l.unit_bytes = l.unit_batches * l.tile_stride;
+    l.stage_bytes = (l.unit_bytes + 127) / 128 * 128;
+    l.batch_stage_bytes = (l.tile_bytes + 127) / 128 * 128;
     *out = l;
     return GSB_OK;
+}
+
+// Bytes of a shard's batches, padded to whole work units (the padding reads as empty rows).
+size_t padded_tile_bytes(const Layout& l, uint32_t n_tiles)
+{
+    const uint32_t units = std::max<uint32_t>(1, (n_tiles + l.unit_batches - 1) / l.unit_batches);
+    return static_cast<size_t>(units) * l.unit_bytes;
 }
 
 struct Workspace {
@@ -129,7 +142,6 @@ struct Shard {
 struct Plan {
     int grid = 0;
     int warps = 0;
-    int unroll = 1;
     uint32_t stages = 0, cap = 0, smem = 0;
 };
 
@@ -177,13 +189,13 @@ int smem_limit(int device, int* out)
     return GSB_OK;
 }
 
-template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
+template <int W, bool RP, int CW> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
     static thread_local int configured[64] = {0};
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
     if (dev < 64 && configured[dev] < static_cast<int>(plan.smem)) {
-        GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP, CW, U>,
+        GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP, CW>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
         configured[dev] = plan.smem;
     }
@@ -191,7 +203,7 @@ template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams
     void* args[] = {const_cast<gsb::ScanParams*>(&p)};
     // (measured: a cooperative launch costs the same as a plain one, 57 us per back-to-back launch
     // at 1 M rows either way)
-    GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_topk_kernel<W, RP, CW, U>), dim3(plan.grid),
+    GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_topk_kernel<W, RP, CW>), dim3(plan.grid),
                                          dim3(CW * 32), args, plan.smem, st));
     g_launches++;
     return GSB_OK;
@@ -199,11 +211,9 @@ template <int W, bool RP, int CW, int U> int launch_scan_t(const gsb::ScanParams
 
 template <int W, bool RP> int launch_scan_w(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
-    // U (batches per iteration) = 1: with 12-16 warps per SM a second in-register batch only adds
-    // register pressure (measured, profiles/r01_sweep.md); the kernel keeps the template knob.
 #define GSB_WCASE(CW)                                                                            \
     case CW:                                                                                     \
-        return launch_scan_t<W, RP, CW, 1>(p, plan, st);
+        return launch_scan_t<W, RP, CW>(p, plan, st);
     switch (plan.warps) {
         GSB_WCASE(4)
         GSB_WCASE(8)
@@ -234,9 +244,8 @@ int launch_scan(const Layout& l, const gsb::ScanParams& p, const Plan& plan, cud
 }
 
 // Warps per CTA, ring depth per warp and candidate capacity for this k.  Rules the kernel
-// relies on: cap is a power of two; cap >= k + 4*U*threads (the select is requested 2*U*threads
-// below the top, and there must be room to refill after it); cap >= k + grid (merge rounds);
-// stages >= U.
+// relies on: cap is a power of two; cap >= k + 4*threads (the select is requested 2*threads below
+// the top, and there must be room to refill after it); cap >= k + grid (merge rounds).
 int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
 {
     int smem_max = 0;
@@ -247,18 +256,20 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
     const int pref = env_int("GSB_WARPS", 16);
     if (pref != 4 && pref != 8 && pref != 12 && pref != 16)
         return fail(GSB_ERR_INVALID, "GSB_WARPS must be 4, 8, 12 or 16");
-    const int want = std::min(gsb::kMaxStages, std::max(2, env_int("GSB_STAGES", 3)));
     // preferred shape first, then fewer stages, then fewer warps (wide rows, large k)
     for (int warps = pref; warps >= 4; warps -= 4) {
+        // ring depth: enough copies in flight per SM (~64 KB) to cover HBM latency — narrow (folded)
+        // rows make small batches and need a deeper ring; 1024-bit rows need two stages
+        const int auto_stages = 1 + static_cast<int>((65536 + warps * l.stage_bytes - 1) / (warps * l.stage_bytes));
+        const int want = std::min(gsb::kMaxStages, std::max(2, env_int("GSB_STAGES", auto_stages)));
         int grid = sh.ws.max_grid;
         if (const int g = env_int("GSB_GRID", 0))
             grid = std::min(g, grid); // never more CTAs than can be resident together
-        const uint32_t n_super = (sh.n_tiles + warps - 1) / warps;
+        const uint32_t n_units = (sh.n_tiles + l.unit_batches - 1) / l.unit_batches;
+        const uint32_t n_super = (n_units + warps - 1) / warps;
         grid = std::max(1, std::min<int>(grid, n_super ? n_super : 1));
         const uint32_t threads = warps * 32;
-        const int unroll = 1;
-        const uint64_t need =
-            std::max<uint64_t>(static_cast<uint64_t>(k) + 4ull * unroll * threads, k + (uint64_t) grid);
+        const uint64_t need = std::max<uint64_t>(static_cast<uint64_t>(k) + 4ull * threads, k + (uint64_t) grid);
         const uint32_t cap = std::max<uint32_t>(pow2ceil(need), static_cast<uint32_t>(env_int("GSB_MIN_CAP", 4096)));
         for (int st = want; st >= 2; st--) {
             const uint64_t smem = static_cast<uint64_t>(warps) * st * l.stage_bytes +
@@ -266,7 +277,6 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
             if (smem <= static_cast<uint64_t>(budget)) {
                 out->grid = grid;
                 out->warps = warps;
-                out->unroll = unroll;
                 out->stages = st;
                 out->cap = cap;
                 out->smem = static_cast<uint32_t>(smem);
@@ -386,7 +396,7 @@ int upload_rows(const gsb_db* db, Shard& sh)
     const Layout& l = db->layout;
     GSB_CUDA(cudaSetDevice(sh.device));
     sh.n_tiles = static_cast<uint32_t>((sh.n_rows + l.tile_rows - 1) / l.tile_rows);
-    sh.bytes = static_cast<size_t>(std::max<uint32_t>(sh.n_tiles, 1)) * l.tile_stride;
+    sh.bytes = padded_tile_bytes(l, sh.n_tiles);
     if (gsb_device_free_bytes(sh.device) <= sh.bytes)
         return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
     GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
@@ -461,9 +471,9 @@ void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k
     p->tiles = sh.tiles;
     p->n_rows = sh.n_rows;
     p->row_base = sh.row_base;
-    p->n_batches = sh.n_tiles;
+    p->n_units = (sh.n_tiles + l.unit_batches - 1) / l.unit_batches;
     p->batch_stride = l.tile_stride;
-    p->batch_bytes = l.tile_bytes;
+    p->unit_bytes = l.unit_bytes;
     p->stage_bytes = l.stage_bytes;
     p->stages = plan.stages;
     p->cap = plan.cap;
@@ -653,7 +663,7 @@ int make_batch_plan(const Layout& l, const Shard& sh, BatchPlan* out)
     const uint64_t fixed = static_cast<uint64_t>(gsb::kMaxBatchQueries) * l.dev_words * 4 + gsb::kBatchListCap * 8ull +
                            gsb::kBuckets * 4ull + gsb::kMaxBatchQueries * (8ull + 8 + 4 + 4);
     for (int warps = 16; warps >= 8; warps -= 8) {
-        const uint64_t smem = static_cast<uint64_t>(warps) * 2 * l.stage_bytes + fixed;
+        const uint64_t smem = static_cast<uint64_t>(warps) * 2 * l.batch_stage_bytes + fixed;
         if (smem + 2048 <= static_cast<uint64_t>(smem_max)) {
             out->warps = warps;
             out->stages = 2;
@@ -756,7 +766,7 @@ int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint3
     p.n_batches = sh.n_tiles;
     p.batch_stride = l.tile_stride;
     p.batch_bytes = l.tile_bytes;
-    p.stage_bytes = l.stage_bytes;
+    p.stage_bytes = l.batch_stage_bytes;
     p.stages = plan.stages;
     p.k = k;
     p.cutoff = cutoff;
@@ -1004,11 +1014,12 @@ int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t r
         return rc;
     const Layout& l = db->layout;
     sh.n_tiles = static_cast<uint32_t>((n_rows + l.tile_rows - 1) / l.tile_rows);
-    sh.bytes = static_cast<size_t>(std::max<uint32_t>(sh.n_tiles, 1)) * l.tile_stride;
+    sh.bytes = padded_tile_bytes(l, sh.n_tiles);
     if (gsb_device_free_bytes(device) <= sh.bytes)
         return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
     GSB_CUDA(cudaSetDevice(device));
     GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
+    GSB_CUDA(cudaMemsetAsync(sh.tiles, 0, sh.bytes, sh.ws.stream)); // padding batches must read as empty rows
     const uint64_t n_words = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows * l.dev_words;
     if (n_words) {
         const uint64_t blocks = (n_words + 255) / 256;
@@ -1423,8 +1434,8 @@ int gsb_db_scan_info(const gsb_db* db, int shard, uint32_t k, gsb_scan_info* out
     out->grid = plan.grid;
     out->block = plan.warps * 32;
     out->stages = plan.stages;
-    out->tile_rows = db->layout.tile_rows;
-    out->tile_bytes = db->layout.tile_bytes;
+    out->tile_rows = db->layout.tile_rows * db->layout.unit_batches;
+    out->tile_bytes = db->layout.unit_bytes;
     out->smem_bytes = plan.smem;
     out->cand_capacity = plan.cap;
     out->shard_rows = sh.n_rows;
