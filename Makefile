@@ -7,7 +7,7 @@ LIB    := gpusimilarity_b200/libgpusim_b200.so
 
 all: $(LIB) adapter oracle
 
-$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
+$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/gsb_sliced.cuh $(CSRC)/gsb_sliced_math.h $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp -lz
 
 # gpusimserver without Qt: same command line as the reference's main.cpp (--cpu_only, --gpu_bitcount)
@@ -28,7 +28,11 @@ tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER)
 	g++ -std=c++14 -O2 -Wall -Iinclude -Ioracle/qt_shims -o $@ tests/cpp/test_adapter.cpp \
 	    -Lgpusimilarity_b200 -lgpusim_adapter -lgpusim_b200 -Wl,-rpath,'$$ORIGIN/../../gpusimilarity_b200'
 
-adapter: $(ADAPTER) tests/cpp/test_adapter $(SERVER)
+# CPU emulation of one warp of the bit-sliced multi-query kernel (layout, transpose, counting)
+tests/cpp/test_sliced_math: tests/cpp/test_sliced_math.cpp $(CSRC)/gsb_sliced_math.h
+	g++ -std=c++14 -O2 -Wall -Werror -o $@ tests/cpp/test_sliced_math.cpp
+
+adapter: $(ADAPTER) tests/cpp/test_adapter tests/cpp/test_sliced_math $(SERVER)
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_api.o $(CSRC)/gsb_api.cu

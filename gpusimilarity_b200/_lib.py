@@ -56,6 +56,7 @@ SIGNATURES = {
     "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
     "gsb_db_search_batch_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_float, _P, _P, _P]),
+    "gsb_db_batch_max_queries": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_float, C.POINTER(C.c_uint32)]),
     "gsb_merge_batch_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_uint32, _P, _P, _P, _P]),
     "gsb_exchange_bytes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gsb_db_search_device_fused": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, C.POINTER(Exchange), _P, _P, _P, _P]),

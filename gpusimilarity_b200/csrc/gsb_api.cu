@@ -7,6 +7,7 @@
 //   get_gpu_count / get_next_gpu / get_available_gpu_memory (fingerprintdb_cuda.cu:33-68,401-413).
 #include "gsb_batch.cuh"
 #include "gsb_kernels.cuh"
+#include "gsb_sliced.cuh"
 
 #include "../../include/gpusim_b200.h"
 #include "gsb_internal.h"
@@ -118,15 +119,23 @@ struct Workspace {
     int max_grid = 0;
     // multi-query kernel scratch (allocated on first use)
     gsb::BatchCtrl* bctrl = nullptr;
-    unsigned long long* bcand = nullptr;   // [grid][kMaxBatchQueries][kBatchListCap]
-    unsigned long long* bqlists = nullptr; // [grid][kMaxBatchQueries][bk_cap]
+    unsigned long long* bcand = nullptr;   // [grid][bnq_cap][kBatchListCap]
+    unsigned long long* bqlists = nullptr; // [grid][bnq_cap][bk_cap]
     uint32_t* bqcounts = nullptr;
     unsigned long long* bsurv = nullptr;
-    uint32_t* bqueries = nullptr;          // [kMaxBatchQueries][dev_words]
-    unsigned long long* bout = nullptr;    // [kMaxBatchQueries][bk_cap + 2] results (+ survivors, n)
+    uint32_t* bqueries = nullptr;          // [bnq_cap][dev_words]
+    unsigned long long* bout = nullptr;    // [bnq_cap][bk_cap + 2] results (+ survivors, n)
     unsigned long long* bout_host = nullptr;
-    uint32_t bk_cap = 0;
+    uint32_t bk_cap = 0, bnq_cap = 0;
     int bgrid = 0;
+    // bit-sliced multi-query kernel: query lists and the sample pass's results
+    uint16_t* slists = nullptr;            // [kMaxSlicedQueries][1024] set-bit entries
+    uint32_t* slofs = nullptr;
+    uint16_t* sngrp = nullptr;
+    uint16_t* spopq = nullptr;
+    gsb::SlicedMeta* smeta = nullptr;
+    unsigned long long* stau = nullptr;    // [kMaxSlicedQueries] thresholds from the sample pass
+    unsigned long long* ssample = nullptr; // [bnq_cap][bk_cap + 2] sample pass results
 };
 
 struct Shard {
@@ -352,6 +361,13 @@ void ws_free(Shard& sh)
     cudaFree(ws.bsurv);
     cudaFree(ws.bqueries);
     cudaFree(ws.bout);
+    cudaFree(ws.ssample);
+    cudaFree(ws.slists);
+    cudaFree(ws.slofs);
+    cudaFree(ws.sngrp);
+    cudaFree(ws.spopq);
+    cudaFree(ws.stau);
+    cudaFree(ws.smeta);
     if (ws.bout_host)
         cudaFreeHost(ws.bout_host);
     cudaFree(sh.tiles);
@@ -643,10 +659,30 @@ int scan_topk(const gsb_db* db, const uint32_t* q_dev_words, uint64_t k_total, f
 }
 
 // ---- multi-query kernel ------------------------------------------------------------------
-bool batch_kernel_applies(const gsb_db* db, uint32_t k, int n_queries)
+// Which multi-query kernel serves a batch.  GSB_BATCH_KERNEL: 0 = none (loop over the single-query
+// kernel), 1 = automatic (default), 2 = POPC kernel, 3 = bit-sliced kernel wherever it applies.
+enum BatchKernel { kBatchNone = 0, kBatchPopc = 1, kBatchSliced = 2 };
+
+BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, float cutoff)
 {
-    return db->layout.rowpop && db->layout.dev_words <= 32 && db->fold_factor == 1 && k >= 1 &&
-           k <= gsb::kMaxBatchK && n_queries >= 2 && env_int("GSB_BATCH_KERNEL", 1) != 0;
+    const int mode = env_int("GSB_BATCH_KERNEL", 1);
+    if (mode == 0 || !db->layout.rowpop || db->layout.dev_words > 32 || db->fold_factor != 1 || k < 1 ||
+        k > gsb::kMaxBatchK || n_queries < 2)
+        return kBatchNone;
+    if (db->layout.dev_words != 32 || mode == 2)
+        return kBatchPopc;
+    if (mode == 3)
+        return kBatchSliced;
+    // The bit-sliced kernel pays a transposition per tile (worth it from ~16 queries on) and scores
+    // every row at or above a positive cutoff exactly (survivor count): low cutoffs let most rows
+    // through and are better served by the POPC kernel.
+    const bool cutoff_ok = !(cutoff > 0.0f) || cutoff >= 0.25f;
+    return n_queries >= 16 && cutoff_ok ? kBatchSliced : kBatchPopc;
+}
+
+uint32_t batch_max_queries(BatchKernel which)
+{
+    return which == kBatchSliced ? gsb::kMaxSlicedQueries : gsb::kMaxBatchQueries;
 }
 
 struct BatchPlan {
@@ -680,37 +716,61 @@ int make_batch_plan(const Layout& l, const Shard& sh, BatchPlan* out)
     return fail(GSB_ERR_INVALID, "no batch launch shape fits");
 }
 
-int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid)
+int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid, uint32_t nq)
 {
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
     if (!ws.bctrl) {
         GSB_CUDA(cudaMalloc(&ws.bctrl, sizeof(gsb::BatchCtrl)));
         GSB_CUDA(cudaMemset(ws.bctrl, 0, sizeof(gsb::BatchCtrl)));
-        GSB_CUDA(cudaMalloc(&ws.bsurv, gsb::kMaxBatchQueries * 8));
-        GSB_CUDA(cudaMemset(ws.bsurv, 0, gsb::kMaxBatchQueries * 8));
-        GSB_CUDA(cudaMalloc(&ws.bqueries, static_cast<size_t>(gsb::kMaxBatchQueries) * l.dev_words * 4));
     }
-    if (grid > ws.bgrid || k > ws.bk_cap) {
+    if (grid > ws.bgrid || k > ws.bk_cap || nq > ws.bnq_cap) {
         cudaFree(ws.bcand);
         cudaFree(ws.bqlists);
         cudaFree(ws.bqcounts);
         cudaFree(ws.bout);
+        cudaFree(ws.bsurv);
+        cudaFree(ws.bqueries);
+        cudaFree(ws.ssample);
         if (ws.bout_host)
             cudaFreeHost(ws.bout_host);
-        ws.bcand = ws.bqlists = ws.bout = ws.bout_host = nullptr;
-        ws.bqcounts = nullptr;
+        ws.bcand = ws.bqlists = ws.bout = ws.bout_host = ws.bsurv = ws.ssample = nullptr;
+        ws.bqcounts = ws.bqueries = nullptr;
         const int g = std::max(grid, ws.bgrid);
         const uint32_t kc = std::max(k, ws.bk_cap);
-        const size_t nq = gsb::kMaxBatchQueries;
-        GSB_CUDA(cudaMalloc(&ws.bcand, static_cast<size_t>(g) * nq * gsb::kBatchListCap * 8));
-        GSB_CUDA(cudaMalloc(&ws.bqlists, static_cast<size_t>(g) * nq * kc * 8));
-        GSB_CUDA(cudaMalloc(&ws.bqcounts, static_cast<size_t>(g) * nq * 4));
-        GSB_CUDA(cudaMalloc(&ws.bout, nq * (kc + 2ull) * 8));
-        GSB_CUDA(cudaMallocHost(&ws.bout_host, nq * (kc + 2ull) * 8));
+        // candidate lists are 16 KB per (CTA, query): grow in steps of 256 queries
+        const size_t nqc = std::max<uint32_t>((nq + 255u) / 256u * 256u, ws.bnq_cap);
+        ws.bgrid = 0;
+        ws.bk_cap = ws.bnq_cap = 0;
+        GSB_CUDA(cudaMalloc(&ws.bcand, static_cast<size_t>(g) * nqc * gsb::kBatchListCap * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqlists, static_cast<size_t>(g) * nqc * kc * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqcounts, static_cast<size_t>(g) * nqc * 4));
+        GSB_CUDA(cudaMalloc(&ws.bout, nqc * (kc + 2ull) * 8));
+        GSB_CUDA(cudaMalloc(&ws.ssample, nqc * (kc + 2ull) * 8));
+        GSB_CUDA(cudaMallocHost(&ws.bout_host, nqc * (kc + 2ull) * 8));
+        GSB_CUDA(cudaMalloc(&ws.bsurv, nqc * 8));
+        GSB_CUDA(cudaMemset(ws.bsurv, 0, nqc * 8));
+        GSB_CUDA(cudaMalloc(&ws.bqueries, nqc * l.dev_words * 4));
         ws.bgrid = g;
         ws.bk_cap = kc;
+        ws.bnq_cap = static_cast<uint32_t>(nqc);
     }
+    return GSB_OK;
+}
+
+int sliced_reserve(Shard& sh)
+{
+    Workspace& ws = sh.ws;
+    if (ws.smeta)
+        return GSB_OK;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    const size_t nq = gsb::kMaxSlicedQueries;
+    GSB_CUDA(cudaMalloc(&ws.slists, nq * 1024 * sizeof(uint16_t)));
+    GSB_CUDA(cudaMalloc(&ws.slofs, nq * sizeof(uint32_t)));
+    GSB_CUDA(cudaMalloc(&ws.sngrp, nq * sizeof(uint16_t)));
+    GSB_CUDA(cudaMalloc(&ws.spopq, nq * sizeof(uint16_t)));
+    GSB_CUDA(cudaMalloc(&ws.stau, nq * sizeof(unsigned long long)));
+    GSB_CUDA(cudaMalloc(&ws.smeta, sizeof(gsb::SlicedMeta)));
     return GSB_OK;
 }
 
@@ -745,20 +805,12 @@ int launch_batch(const Layout& l, const gsb::BatchParams& p, const BatchPlan& pl
     }
 }
 
-// One launch over one shard for nq <= kMaxBatchQueries queries already in device memory.
-// Results: out_keys [nq][k], out_survivors [nq], out_n [nq].
-int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
-                       float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
+void fill_batch_params(const gsb_db* db, const Shard& sh, uint32_t nq, uint32_t k, float cutoff,
+                       const uint32_t* d_queries, unsigned long long* out_keys, uint32_t* out_n,
+                       unsigned long long* out_surv, gsb::BatchParams* out)
 {
-    BatchPlan plan;
-    int rc = make_batch_plan(db->layout, sh, &plan);
-    if (rc)
-        return rc;
-    rc = batch_reserve(sh, db->layout, k, plan.grid);
-    if (rc)
-        return rc;
     const Layout& l = db->layout;
-    gsb::BatchParams p;
+    gsb::BatchParams& p = *out;
     std::memset(&p, 0, sizeof(p));
     p.tiles = sh.tiles;
     p.n_rows = sh.n_rows;
@@ -767,7 +819,6 @@ int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint3
     p.batch_stride = l.tile_stride;
     p.batch_bytes = l.tile_bytes;
     p.stage_bytes = l.batch_stage_bytes;
-    p.stages = plan.stages;
     p.k = k;
     p.cutoff = cutoff;
     p.nq = nq;
@@ -780,18 +831,113 @@ int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint3
     p.out_keys = out_keys;
     p.out_n = out_n;
     p.out_survivors = out_surv;
-    GSB_CUDA(cudaSetDevice(sh.device));
-    return launch_batch(l, p, plan, st);
 }
 
-// Host-buffer batch over every shard: groups of up to kMaxBatchQueries queries per launch.
-int search_batch_kernel_path(const gsb_db* db, const int32_t* query_words, int n_queries, uint32_t k, float cutoff,
-                             uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+// Bit-sliced kernel over one shard (gsb_sliced.cuh): query lists, a strided sample pass that
+// yields a threshold per query, then the full pass.  Everything is queued on `st`.
+int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
+                        float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
+{
+    constexpr int kWarps = 16;
+    int smem_max = 0, sms = 0;
+    int rc = smem_limit(sh.device, &smem_max);
+    if (rc)
+        return rc;
+    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+    const uint32_t nqp = (nq + 7u) & ~7u;
+    const uint32_t smem = gsb::kSlicedTileBytes + gsb::kSlicedTileBatches * gsb::kBatchRows * 2 +
+                          gsb::kSlicedListEntries * 2 + nqp * gsb::kSlicedPerQueryBytes;
+    if (smem + 2048 > static_cast<uint32_t>(smem_max))
+        return fail(GSB_ERR_INVALID, "the bit-sliced multi-query kernel does not fit this device's shared memory");
+    const uint32_t n_tiles = (sh.n_tiles + gsb::kSlicedTileBatches - 1) / gsb::kSlicedTileBatches;
+    int grid = std::max(1, std::min<int>(sms, n_tiles)); // all CTAs resident: grid-wide arrival counter
+    if (const int g = env_int("GSB_GRID", 0))
+        grid = std::max(1, std::min(grid, g));
+    rc = batch_reserve(sh, db->layout, k, grid, nq);
+    if (rc)
+        return rc;
+    rc = sliced_reserve(sh);
+    if (rc)
+        return rc;
+    Workspace& ws = sh.ws;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    gsb::sliced_build_lists_kernel<<<1, gsb::kMaxSlicedQueries, 0, st>>>(d_queries, nq, ws.slists, ws.slofs, ws.sngrp,
+                                                                         ws.spopq, ws.smeta);
+    g_launches++;
+    GSB_CUDA(cudaGetLastError());
+    GSB_CUDA(cudaFuncSetAttribute(gsb::scan_sliced_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    gsb::SlicedParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.lists = ws.slists;
+    sp.lofs = ws.slofs;
+    sp.ngrp = ws.sngrp;
+    sp.popq = ws.spopq;
+    sp.meta = ws.smeta;
+    auto launch = [&]() -> int {
+        void* args[] = {&sp};
+        GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_sliced_kernel<kWarps>), dim3(grid),
+                                             dim3(kWarps * 32), args, smem, st));
+        g_launches++;
+        return GSB_OK;
+    };
+    // ---- sample pass: every step-th tile, ~1.5 % of the shard but at least 4 tiles per CTA; its
+    // k-th key per query (minus one, so that the key itself stays eligible) seeds the full pass
+    const uint32_t sample_claims = std::max<uint32_t>(4u * grid, n_tiles / 64u);
+    const bool sample = env_int("GSB_SLICED_SAMPLE", 1) != 0 && static_cast<uint64_t>(sample_claims) * 4u <= n_tiles;
+    if (sample) {
+        unsigned long long* skeys = ws.ssample;
+        unsigned long long* ssurv = skeys + static_cast<size_t>(nq) * k;
+        uint32_t* scnt = reinterpret_cast<uint32_t*>(ssurv + nq);
+        fill_batch_params(db, sh, nq, k, cutoff, d_queries, skeys, scnt, ssurv, &sp.b);
+        sp.tau_init = nullptr;
+        sp.n_claims = sample_claims;
+        sp.tile_step = n_tiles / sample_claims;
+        rc = launch();
+        if (rc)
+            return rc;
+        gsb::sliced_seed_tau_kernel<<<(nq + 255) / 256, 256, 0, st>>>(skeys, scnt, nq, k, ws.stau);
+        g_launches++;
+        GSB_CUDA(cudaGetLastError());
+    }
+    fill_batch_params(db, sh, nq, k, cutoff, d_queries, out_keys, out_n, out_surv, &sp.b);
+    sp.tau_init = sample ? ws.stau : nullptr;
+    sp.n_claims = n_tiles;
+    sp.tile_step = 1;
+    return launch();
+}
+
+// One pass over one shard for nq <= batch_max_queries(which) queries already in device memory.
+// Results: out_keys [nq][k], out_survivors [nq], out_n [nq].
+int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, BatchKernel which, const uint32_t* d_queries,
+                       uint32_t nq, uint32_t k, float cutoff, unsigned long long* out_keys, uint32_t* out_n,
+                       unsigned long long* out_surv)
+{
+    if (which == kBatchSliced)
+        return sliced_launch_shard(db, sh, st, d_queries, nq, k, cutoff, out_keys, out_n, out_surv);
+    BatchPlan plan;
+    int rc = make_batch_plan(db->layout, sh, &plan);
+    if (rc)
+        return rc;
+    rc = batch_reserve(sh, db->layout, k, plan.grid, nq);
+    if (rc)
+        return rc;
+    gsb::BatchParams p;
+    fill_batch_params(db, sh, nq, k, cutoff, d_queries, out_keys, out_n, out_surv, &p);
+    p.stages = plan.stages;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    return launch_batch(db->layout, p, plan, st);
+}
+
+// Host-buffer batch over every shard: groups of up to batch_max_queries(which) queries per pass.
+int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t* query_words, int n_queries, uint32_t k,
+                             float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
 {
     const Layout& l = db->layout;
     const uint32_t words = db->words;
-    for (int q0 = 0; q0 < n_queries; q0 += gsb::kMaxBatchQueries) {
-        const uint32_t nq = static_cast<uint32_t>(std::min<int>(gsb::kMaxBatchQueries, n_queries - q0));
+    const int group = static_cast<int>(batch_max_queries(which));
+    for (int q0 = 0; q0 < n_queries; q0 += group) {
+        const uint32_t nq = static_cast<uint32_t>(std::min<int>(group, n_queries - q0));
         std::vector<uint32_t> padded(static_cast<size_t>(nq) * l.dev_words, 0u);
         for (uint32_t j = 0; j < nq; j++)
             std::memcpy(padded.data() + static_cast<size_t>(j) * l.dev_words,
@@ -800,20 +946,20 @@ int search_batch_kernel_path(const gsb_db* db, const int32_t* query_words, int n
             Shard& sh = const_cast<Shard&>(db->shards[i]);
             if (sh.n_rows == 0)
                 continue;
-            BatchPlan plan;
-            int rc = make_batch_plan(l, sh, &plan);
-            if (rc)
-                return rc;
-            rc = batch_reserve(sh, l, k, plan.grid);
+            // reserve for the largest grid a launch can use (one CTA per SM), so that the launch
+            // itself never re-allocates the buffers the queries are being copied into
+            int sms = 0;
+            GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+            int rc = batch_reserve(sh, l, k, sms, nq);
             if (rc)
                 return rc;
             GSB_CUDA(cudaSetDevice(sh.device));
             GSB_CUDA(cudaMemcpyAsync(sh.ws.bqueries, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice,
                                      sh.ws.stream));
             unsigned long long* keys = sh.ws.bout;
-            unsigned long long* surv = sh.ws.bout + static_cast<size_t>(nq) * k;
+            unsigned long long* surv = keys + static_cast<size_t>(nq) * k;
             uint32_t* cnt = reinterpret_cast<uint32_t*>(surv + nq);
-            rc = batch_launch_shard(db, sh, sh.ws.stream, sh.ws.bqueries, nq, k, cutoff, keys, cnt, surv);
+            rc = batch_launch_shard(db, sh, sh.ws.stream, which, sh.ws.bqueries, nq, k, cutoff, keys, cnt, surv);
             if (rc)
                 return rc;
             GSB_CUDA(cudaMemcpyAsync(sh.ws.bout_host, sh.ws.bout, (static_cast<size_t>(nq) * (k + 2ull)) * 8,
@@ -1204,9 +1350,13 @@ int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_word
     if (n_queries < 0)
         return fail(GSB_ERR_INVALID, "negative query count");
     if (db && query_words && out_rows && out_scores && out_n && db->uploaded &&
-        n_words == static_cast<int>(db->words) && batch_kernel_applies(db, k, n_queries)) {
-        std::lock_guard<std::mutex> lock(db->mu);
-        return search_batch_kernel_path(db, query_words, n_queries, k, cutoff, out_rows, out_scores, out_n, out_approx);
+        n_words == static_cast<int>(db->words)) {
+        const BatchKernel which = batch_kernel_choice(db, k, n_queries, cutoff);
+        if (which != kBatchNone) {
+            std::lock_guard<std::mutex> lock(db->mu);
+            return search_batch_kernel_path(db, which, query_words, n_queries, k, cutoff, out_rows, out_scores, out_n,
+                                            out_approx);
+        }
     }
     for (int qi = 0; qi < n_queries; qi++) {
         int rc = gsb_db_search(db, query_words + static_cast<size_t>(qi) * n_words, n_words, k, cutoff,
@@ -1295,17 +1445,30 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
         return fail(GSB_ERR_INVALID, "null argument");
     if (!db->uploaded || db->shards.size() != 1)
         return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
-    if (n_queries < 1 || n_queries > static_cast<int>(gsb::kMaxBatchQueries))
-        return fail(GSB_ERR_INVALID, "1..256 queries per launch");
     if (!db->layout.rowpop || db->layout.dev_words > 32 || db->layout.dev_words != db->words || db->fold_factor != 1 ||
         k < 1 || k > gsb::kMaxBatchK)
-        return fail(GSB_ERR_INVALID, "the multi-query kernel needs the default layout, <= 1024 bits, k <= 512");
+        return fail(GSB_ERR_INVALID, "the multi-query kernels need the default layout, <= 1024 bits, k <= 512");
+    BatchKernel which = batch_kernel_choice(db, k, std::max(n_queries, 2), cutoff);
+    if (which == kBatchNone)
+        which = kBatchPopc; // GSB_BATCH_KERNEL=0 only switches the host-buffer API to looping
+    if (n_queries < 1 || n_queries > static_cast<int>(batch_max_queries(which)))
+        return fail(GSB_ERR_INVALID, "1..256 queries per call (1..1024 where the bit-sliced kernel applies: "
+                                     "1024-bit rows, 16 or more queries, cutoff <= 0 or >= 0.25)");
     std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
-    return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), reinterpret_cast<const uint32_t*>(d_queries),
-                              static_cast<uint32_t>(n_queries), k, cutoff,
+    return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), which,
+                              reinterpret_cast<const uint32_t*>(d_queries), static_cast<uint32_t>(n_queries), k, cutoff,
                               reinterpret_cast<unsigned long long*>(d_out_keys), d_out_n,
                               reinterpret_cast<unsigned long long*>(d_out_survivors));
+}
+
+int gsb_db_batch_max_queries(const gsb_db* db, uint32_t k, int n_queries, float cutoff, uint32_t* out_max)
+{
+    if (!db || !out_max)
+        return fail(GSB_ERR_INVALID, "null argument");
+    BatchKernel which = batch_kernel_choice(db, k, std::max(n_queries, 2), cutoff);
+    *out_max = batch_max_queries(which == kBatchNone ? kBatchPopc : which);
+    return GSB_OK;
 }
 
 int gsb_merge_batch_device(int device, void* stream, const gsb_key* d_records, int n_ranks, int n_queries, uint32_t k,

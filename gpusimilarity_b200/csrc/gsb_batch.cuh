@@ -46,6 +46,111 @@ struct BatchParams {
     unsigned long long* out_survivors;  // [nq]
 };
 
+// Cut back every candidate list of this CTA that is more than half full (or, with exact_all, cut
+// every list to its exact sorted top k).  All NT threads; lists are staged through cs.buf.
+// tau_raised(j) runs on thread 0 after s_tau[j] went up.
+template <int NT, class F>
+__device__ void batch_select_round(const CandShared& cs, unsigned long long* my_cand, unsigned int* s_cnt,
+                                   unsigned long long* s_tau, uint32_t nq, uint32_t k, bool exact_all, uint32_t tid,
+                                   F tau_raised)
+{
+    cta_sync<NT>();
+    for (uint32_t j = 0; j < nq; j++) {
+        const uint32_t n = s_cnt[j] < kBatchListCap ? s_cnt[j] : kBatchListCap;
+        if (!exact_all && n <= kBatchListCap / 2)
+            continue;
+        unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
+        for (uint32_t i = tid; i < n; i += NT)
+            cs.buf[i] = list[i];
+        if (tid == 0) {
+            *cs.count = n;
+            *cs.tau = 0;
+        }
+        cand_compact<NT>(cs, k, nullptr, tid, exact_all);
+        const uint32_t kept = *cs.count;
+        for (uint32_t i = tid; i < kept; i += NT)
+            list[i] = cs.buf[i];
+        if (tid == 0) {
+            s_cnt[j] = kept;
+            if (*cs.tau > s_tau[j]) {
+                s_tau[j] = *cs.tau;
+                tau_raised(j);
+            }
+        }
+        cta_sync<NT>();
+    }
+}
+
+// End of a multi-query launch, all NT threads of every CTA: exact sorted top-k of every list to
+// global memory, grid-wide arrival (cooperative launch: all CTAs resident), per-query merges
+// spread over the CTAs, and the last CTA leaves the control block clean.
+template <int NT>
+__device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigned long long* my_cand,
+                             unsigned int* s_cnt, unsigned long long* s_tau, const unsigned long long* s_surv,
+                             unsigned int* s_alive, uint32_t tid)
+{
+    const uint32_t nq = p.nq;
+    const bool drop_zero = p.cutoff > 0.0f;
+    __threadfence_block();
+    batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, true, tid, [](uint32_t) {});
+    for (uint32_t j = 0; j < nq; j++) {
+        const uint32_t n = s_cnt[j];
+        const unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
+        unsigned long long* dst = p.qlists + ((uint64_t) blockIdx.x * nq + j) * p.k;
+        for (uint32_t i = tid; i < n; i += NT)
+            dst[i] = list[i];
+        if (tid == 0) {
+            p.qcounts[blockIdx.x * nq + j] = n;
+            if (drop_zero && s_surv[j])
+                atomicAdd(&p.surv_acc[j], s_surv[j]);
+        }
+    }
+    __threadfence();
+    cta_sync<NT>();
+    // ---- grid-wide arrival (the grid is persistent: one CTA per SM, all resident)
+    if (tid == 0) {
+        atomicAdd(&p.ctrl->ticket, 1u);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < gridDim.x) {
+            if (clock64() - t0 > (200ll << 30)) // ~100 s (CTAs finish far apart here); fail loudly, never hang
+                __trap();
+        }
+        __threadfence();
+    }
+    cta_sync<NT>();
+    // ---- merges, spread over the CTAs: query j is merged by CTA j % grid
+    for (uint32_t j = blockIdx.x; j < nq; j += gridDim.x) {
+        merge_lists<NT>(cs, p.qlists + (uint64_t) j * p.k, p.qcounts + j, gridDim.x, nq * p.k, p.k, 0ull, s_alive, tid,
+                        nq);
+        const uint32_t n = *cs.count;
+        for (uint32_t i = tid; i < p.k; i += NT)
+            p.out_keys[(uint64_t) j * p.k + i] = i < n ? cs.buf[i] : 0ull;
+        if (tid == 0) {
+            p.out_n[j] = n;
+            p.out_survivors[j] = drop_zero ? *reinterpret_cast<volatile unsigned long long*>(&p.surv_acc[j]) : p.n_rows;
+        }
+        cta_sync<NT>();
+    }
+    // ---- the last CTA to finish leaves the control block and accumulators clean
+    __threadfence();
+    cta_sync<NT>();
+    if (tid == 0) {
+        const unsigned d = atomicAdd(&p.ctrl->done, 1u);
+        *s_alive = (d == gridDim.x - 1) ? 1u : 0u;
+    }
+    cta_sync<NT>();
+    if (*s_alive) {
+        for (uint32_t j = tid; j < nq; j += NT)
+            p.surv_acc[j] = 0;
+        if (tid == 0) {
+            p.ctrl->next_batch = 0;
+            p.ctrl->done = 0;
+            __threadfence();
+            p.ctrl->ticket = 0;
+        }
+    }
+}
+
 template <int W, int CW>
 __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_constant__ BatchParams p)
 {
@@ -151,31 +256,8 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     }
     __syncthreads();
 
-    // Cut back every list that is more than half full (all threads; staged through shared memory).
-    auto select_round = [&](bool exact_all) {
-        cta_sync<NT>();
-        for (uint32_t j = 0; j < nq; j++) {
-            const uint32_t n = s_cnt[j] < kBatchListCap ? s_cnt[j] : kBatchListCap;
-            if (!exact_all && n <= kBatchListCap / 2)
-                continue;
-            unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
-            for (uint32_t i = tid; i < n; i += NT)
-                s_buf[i] = list[i];
-            if (tid == 0) {
-                s_stage_count = n;
-                s_stage_tau = 0;
-            }
-            cand_compact<NT>(cs, p.k, nullptr, tid, exact_all);
-            const uint32_t kept = s_stage_count;
-            for (uint32_t i = tid; i < kept; i += NT)
-                list[i] = s_buf[i];
-            if (tid == 0) {
-                s_cnt[j] = kept;
-                if (s_stage_tau > s_tau[j])
-                    s_tau[j] = s_stage_tau;
-            }
-            cta_sync<NT>();
-        }
+    auto select_round = [&]() {
+        batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, tid, [](uint32_t) {});
     };
 
     const bool drop_zero = p.cutoff > 0.0f;
@@ -186,7 +268,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
 
     for (;;) {
         if (warp_uniform_ld(&s_epoch_req) > my_epoch) {
-            select_round(false);
+            select_round();
             my_epoch++;
         }
         const uint32_t bid = *reinterpret_cast<volatile uint32_t*>(&my_bid[stage]);
@@ -255,7 +337,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     }
     for (;;) {
         if (warp_uniform_ld(&s_epoch_req) > my_epoch) {
-            select_round(false);
+            select_round();
             my_epoch++;
             continue;
         }
@@ -266,65 +348,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
             break;
         }
     }
-    // ---- per-CTA results: exact top-k of every list, sorted, to global memory
-    __threadfence_block();
-    select_round(true);
-    for (uint32_t j = 0; j < nq; j++) {
-        const uint32_t n = s_cnt[j];
-        const unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
-        unsigned long long* dst = p.qlists + ((uint64_t) blockIdx.x * nq + j) * p.k;
-        for (uint32_t i = tid; i < n; i += NT)
-            dst[i] = list[i];
-        if (tid == 0) {
-            p.qcounts[blockIdx.x * nq + j] = n;
-            if (drop_zero && s_surv[j])
-                atomicAdd(&p.surv_acc[j], s_surv[j]);
-        }
-    }
-    __threadfence();
-    cta_sync<NT>();
-    // ---- grid-wide arrival (the grid is persistent: one CTA per SM, all resident)
-    if (tid == 0) {
-        atomicAdd(&p.ctrl->ticket, 1u);
-        const long long t0 = clock64();
-        while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < gridDim.x) {
-            if (clock64() - t0 > (200ll << 30)) // ~100 s (CTAs finish far apart here); fail loudly, never hang
-                __trap();
-        }
-        __threadfence();
-    }
-    cta_sync<NT>();
-    // ---- merges, spread over the CTAs: query j is merged by CTA j % grid
-    for (uint32_t j = blockIdx.x; j < nq; j += gridDim.x) {
-        merge_lists<NT>(cs, p.qlists + (uint64_t) j * p.k, p.qcounts + j, gridDim.x, nq * p.k, p.k, 0ull, &s_alive, tid,
-                        nq);
-        const uint32_t n = s_stage_count;
-        for (uint32_t i = tid; i < p.k; i += NT)
-            p.out_keys[(uint64_t) j * p.k + i] = i < n ? s_buf[i] : 0ull;
-        if (tid == 0) {
-            p.out_n[j] = n;
-            p.out_survivors[j] = drop_zero ? *reinterpret_cast<volatile unsigned long long*>(&p.surv_acc[j]) : p.n_rows;
-        }
-        cta_sync<NT>();
-    }
-    // ---- the last CTA to finish leaves the control block and accumulators clean
-    __threadfence();
-    cta_sync<NT>();
-    if (tid == 0) {
-        const unsigned d = atomicAdd(&p.ctrl->done, 1u);
-        s_alive = (d == gridDim.x - 1) ? 1u : 0u;
-    }
-    cta_sync<NT>();
-    if (s_alive) {
-        for (uint32_t j = tid; j < nq; j += NT)
-            p.surv_acc[j] = 0;
-        if (tid == 0) {
-            p.ctrl->next_batch = 0;
-            p.ctrl->done = 0;
-            __threadfence();
-            p.ctrl->ticket = 0;
-        }
-    }
+    batch_finish<NT>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, tid);
 }
 
 // Merge of all-gathered per-rank batch records: one CTA per query.  Record layout per rank:

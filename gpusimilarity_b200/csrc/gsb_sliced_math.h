@@ -1,0 +1,165 @@
+// Pure integer helpers of the bit-sliced multi-query scan (gsb_sliced.cuh).  Host and device:
+// tests/cpp/test_sliced_math.cpp emulates a warp with them on the CPU (layout, swizzle, transpose,
+// carry-save counting, bit-sliced compare) against plain popcounts.
+//
+// The idea: the scores of one query against 32 rows need common = popc(q & d) per row (reference
+// TanimotoFunctor, fingerprintdb_cuda.cu:97-98).  With a 32-row batch stored bit-transposed —
+// word T[pos] holds bit `pos` of each of the 32 rows — common for all 32 rows at once is the
+// column sum of the words T[pos] over the SET bits of q only (~40 of 1024 for Morgan
+// fingerprints), accumulated with carry-save adders into bit-sliced counters: a handful of LOP3
+// per set bit and 32 rows instead of 32 AND + 32 POPC per row.
+#pragma once
+
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define GSB_HD __host__ __device__ __forceinline__
+#else
+#define GSB_HD inline
+#endif
+#ifdef __CUDA_ARCH__
+#define GSB_UNROLL _Pragma("unroll")
+#else
+#define GSB_UNROLL
+#endif
+
+namespace gsb
+{
+
+constexpr uint32_t kSlicedTileBatches = 32;   // 32-row batches per tile: lane l of a warp works on batch l
+constexpr uint32_t kSlicedRegionBytes = 4224; // shared memory per batch: 1025 transposed words + lane skew
+constexpr uint32_t kSlicedZeroPos = 1024;     // bit position whose word is always zero (list padding)
+constexpr uint32_t kSlicedGroup = 8;          // list entries consumed per carry-save round
+constexpr uint32_t kSlicedMaxPlanes = 11;     // common <= 1024
+
+// Word index of bit position `pos` (0..1024) inside a lane's transposed batch.  The rotation by
+// the word column (pos >> 5) makes the transposition's stores conflict free (lane = column writes
+// 32 words that land in 32 banks); lane l's batch starts 4*l bytes into its region, so the loads
+// of one position by the 32 lanes of a warp hit 32 different banks as well.
+GSB_HD uint32_t sliced_word_index(uint32_t pos)
+{
+    return (pos & ~31u) | ((pos + (pos >> 5)) & 31u);
+}
+// List entry: byte offset of the position's word from the lane's batch base.
+GSB_HD uint16_t sliced_entry(uint32_t pos)
+{
+    return static_cast<uint16_t>(sliced_word_index(pos) * 4u);
+}
+// Byte offset of lane l's transposed batch inside the tile buffer.
+GSB_HD uint32_t sliced_lane_base(uint32_t l)
+{
+    return l * kSlicedRegionBytes + 4u * l;
+}
+
+template <int J, uint32_t M> GSB_HD void transpose32_stage(uint32_t (&a)[32])
+{
+GSB_UNROLL
+    for (int k0 = 0; k0 < 32; k0 += 2 * J) {
+GSB_UNROLL
+        for (int i = 0; i < J; i++) {
+            const int k = k0 + i;
+            const uint32_t t = ((a[k] >> J) ^ a[k + J]) & M;
+            a[k + J] ^= t;
+            a[k] ^= t << J;
+        }
+    }
+}
+// 32x32 bit-matrix transpose in registers: afterwards bit r of a[b] is bit b of the old a[r].
+GSB_HD void transpose32(uint32_t (&a)[32])
+{
+    transpose32_stage<16, 0x0000ffffu>(a);
+    transpose32_stage<8, 0x00ff00ffu>(a);
+    transpose32_stage<4, 0x0f0f0f0fu>(a);
+    transpose32_stage<2, 0x33333333u>(a);
+    transpose32_stage<1, 0x55555555u>(a);
+}
+
+// Carry-save adder over 32 independent bit columns: a + b + c = 2*h + l.
+GSB_HD void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t u = a ^ b;
+    h = (a & b) | (u & c);
+    l = u ^ c;
+}
+
+// Running bit-sliced counters of one lane: column r of (ones, twos, fours, hi[0..NP)) is the number
+// of words added so far that had bit r set.
+template <int NP> struct SlicedCount {
+    uint32_t ones = 0, twos = 0, fours = 0;
+    uint32_t hi[NP];
+    GSB_HD SlicedCount()
+    {
+        for (int i = 0; i < NP; i++)
+            hi[i] = 0;
+    }
+    // add eight words (Harley-Seal round: 7 carry-save adders, then the carry out ripples into hi)
+    GSB_HD void add8(uint32_t x0, uint32_t x1, uint32_t x2, uint32_t x3, uint32_t x4, uint32_t x5, uint32_t x6,
+                     uint32_t x7)
+    {
+        uint32_t ta, tb, fa, fb, eights;
+        csa(ta, ones, ones, x0, x1);
+        csa(tb, ones, ones, x2, x3);
+        csa(fa, twos, twos, ta, tb);
+        csa(ta, ones, ones, x4, x5);
+        csa(tb, ones, ones, x6, x7);
+        csa(fb, twos, twos, ta, tb);
+        csa(eights, fours, fours, fa, fb);
+        uint32_t carry = eights;
+GSB_UNROLL
+        for (int i = 0; i < NP; i++) {
+            const uint32_t t = hi[i] & carry;
+            hi[i] ^= carry;
+            carry = t;
+        }
+    }
+    GSB_HD uint32_t plane(int p) const
+    {
+        return p == 0 ? ones : (p == 1 ? twos : (p == 2 ? fours : hi[p - 3]));
+    }
+    // columns whose count is >= m (m < 2^(3+NP)): bit-sliced compare against a constant
+    GSB_HD uint32_t at_least(uint32_t m) const
+    {
+        uint32_t gt = 0, eq = ~0u;
+GSB_UNROLL
+        for (int p = 3 + NP - 1; p >= 0; p--) {
+            const uint32_t c = plane(p);
+            if ((m >> p) & 1u) {
+                eq &= c;
+            } else {
+                gt |= eq & c;
+                eq &= ~c;
+            }
+        }
+        return gt | eq;
+    }
+    // count of column r
+    GSB_HD uint32_t column(uint32_t r) const
+    {
+        uint32_t c = 0;
+GSB_UNROLL
+        for (int p = 0; p < 3 + NP; p++)
+            c |= ((plane(p) >> r) & 1u) << p;
+        return c;
+    }
+};
+
+// Smallest common-bit count that can still reach score `ts` for a query of `pq` set bits: the
+// union is at least pq, so score <= div(common, pq); rows below the returned count are skipped
+// without being scored.  `div` is the kernel's correctly rounded division (monotone in common).
+// Returns pq + 1 (or more) when nothing can pass.
+template <class Div> GSB_HD uint32_t sliced_filter_min(float ts, uint32_t pq, Div div)
+{
+    if (!(ts > 0.0f))
+        return 0;
+    if (pq == 0)
+        return 1; // every score is 0/0 -> 0 (fingerprintdb_cuda.cu:102), below any positive ts
+    const float est = ts * static_cast<float>(pq);
+    uint32_t m = est >= 2.0f ? static_cast<uint32_t>(est) - 1u : 0u;
+    if (m > pq)
+        m = pq;
+    while (m <= pq && !(div(m, pq) >= ts))
+        m++;
+    return m;
+}
+
+} // namespace gsb

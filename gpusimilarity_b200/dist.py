@@ -140,10 +140,11 @@ class ShardedSearcher:
 
 class ShardedBatchSearcher:
     """Multi-query variant (BASELINE config "1024 queries, top-100, 8 GPUs"): every rank scores its
-    shard against up to 256 queries per launch (gsb_db_search_batch_device), the per-rank records
+    shard against up to 1024 queries per pass (gsb_db_search_batch_device: bit-sliced kernel; 256
+    where only the POPC kernel applies, see max_queries), the per-rank records
     ([nq][k] keys, [nq] survivors, [nq] counts) are all-gathered and merged with one CTA per query."""
 
-    MAX_QUERIES = 256
+    MAX_QUERIES = 1024
 
     def __init__(self, db, k: int, local_device: int, dist=None, world: int = 1):
         import torch
@@ -156,6 +157,14 @@ class ShardedBatchSearcher:
         self.out_scores = torch.zeros(nq * k, dtype=torch.float32, device=dev)
         self.out_n = torch.zeros(nq, dtype=torch.int32, device=dev)
         self.out_approx = torch.zeros(nq, dtype=torch.int64, device=dev)
+
+    def max_queries(self, n_queries: int, cutoff: float) -> int:
+        """Queries one search_device call accepts for this batch size and cutoff."""
+        import ctypes as C
+        from ._lib import check, lib
+        out = C.c_uint32(0)
+        check(lib().gsb_db_batch_max_queries(self.db._h, self.k, n_queries, cutoff, C.byref(out)))
+        return int(out.value)
 
     def search_device(self, d_queries_ptr: int, n_queries: int, cutoff: float, stream) -> None:
         """Results for queries [0, n_queries) stay in HBM: out_rows/out_scores [nq][k], out_n, out_approx."""

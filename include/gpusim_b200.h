@@ -92,8 +92,10 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
 /* New (the reference serves one query per request, gpusim.cpp:407-414): n_queries queries
  * over the same database; query q's results land at out_rows + q*k etc.  Identical results to
  * n_queries calls of gsb_db_search.  With the default layout, rows of at most 1024 bits, no fold
- * and k <= 512 the queries share ONE pass over the database per group of 256 (multi-query
- * kernel, POPC-bound instead of HBM-bound); otherwise they are searched one after the other. */
+ * and k <= 512 the queries share ONE pass over the database per group: 1024 queries per pass
+ * with the bit-sliced kernel (1024-bit rows, 16 or more queries, cutoff <= 0 or >= 0.25;
+ * gsb_sliced.cuh), 256 with the POPC kernel; otherwise they are searched one after the other.
+ * GSB_BATCH_KERNEL=0/2/3 forces looping / the POPC kernel / the bit-sliced kernel. */
 int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words,
                         int n_queries, uint32_t k, float cutoff, uint32_t* out_rows,
                         float* out_scores, uint32_t* out_n, uint64_t* out_approx);
@@ -123,13 +125,17 @@ int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint
                      int n_lists, uint32_t list_stride, uint32_t k, uint32_t* d_out_rows,
                      float* d_out_scores, uint32_t* d_out_n);
 
-/* Multi-query scan of this process's shard: n_queries (1..256) queries in device memory
+/* Multi-query scan of this process's shard: n_queries queries in device memory
  * ([n_queries][fp_bits/32] words) are scored against every row in ONE pass over the database.
  * d_out_keys [n_queries][k] (best first, zero padded), d_out_n [n_queries], d_out_survivors
- * [n_queries].  Needs the default layout, fingerprints of at most 1024 bits and k <= 512. */
+ * [n_queries].  Needs the default layout, fingerprints of at most 1024 bits and k <= 512.
+ * n_queries is limited to gsb_db_batch_max_queries() per call. */
 int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_queries, int n_queries,
                                uint32_t k, float cutoff, gsb_key* d_out_keys, uint32_t* d_out_n,
                                uint64_t* d_out_survivors);
+/* Queries one gsb_db_search_batch_device call accepts for this k / batch size / cutoff: 1024
+ * where the bit-sliced kernel applies (see gsb_db_search_batch), else 256. */
+int gsb_db_batch_max_queries(const gsb_db* db, uint32_t k, int n_queries, float cutoff, uint32_t* out_max);
 /* Merge of all-gathered per-rank batch records (per rank: [n_queries][k] keys, [n_queries]
  * survivors, [n_queries] counts, u64 each): one CTA per query. */
 int gsb_merge_batch_device(int device, void* stream, const gsb_key* d_records, int n_ranks, int n_queries,

@@ -1,0 +1,188 @@
+// CPU emulation of one warp of the bit-sliced multi-query scan (gsb_sliced.cuh) with the shared
+// integer helpers: tile layout, transposition, bank-conflict freedom, carry-save counting,
+// bit-sliced compare and the filter bound, against plain popcounts.  Exit code 0 = all good.
+#include "../../gpusimilarity_b200/csrc/gsb_sliced_math.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <set>
+#include <vector>
+
+using namespace gsb;
+
+static int g_fail = 0;
+#define CHECK(c)                                                                                 \
+    do {                                                                                         \
+        if (!(c)) {                                                                              \
+            if (g_fail++ < 20)                                                                   \
+                std::fprintf(stderr, "FAIL %s:%d %s\n", __FILE__, __LINE__, #c);                 \
+        }                                                                                        \
+    } while (0)
+
+static uint32_t rd32(const std::vector<uint8_t>& b, size_t off)
+{
+    uint32_t v;
+    std::memcpy(&v, &b[off], 4);
+    return v;
+}
+static void wr32(std::vector<uint8_t>& b, size_t off, uint32_t v)
+{
+    std::memcpy(&b[off], &v, 4);
+}
+
+template <int NP>
+static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint32_t>& rows, std::mt19937& rng,
+                        int n_queries, double density)
+{
+    std::bernoulli_distribution bit(density);
+    for (int qi = 0; qi < n_queries; qi++) {
+        uint32_t q[32];
+        for (int w = 0; w < 32; w++) {
+            q[w] = 0;
+            for (int b = 0; b < 32; b++)
+                q[w] |= static_cast<uint32_t>(bit(rng)) << b;
+        }
+        // list of entries, padded to a multiple of kSlicedGroup with the zero position
+        std::vector<uint16_t> list;
+        for (int w = 0; w < 32; w++)
+            for (int b = 0; b < 32; b++)
+                if ((q[w] >> b) & 1u)
+                    list.push_back(sliced_entry(w * 32 + b));
+        const uint32_t pq = static_cast<uint32_t>(list.size());
+        while (list.size() % kSlicedGroup)
+            list.push_back(sliced_entry(kSlicedZeroPos));
+        if (pq >= (1u << (3 + NP)))
+            continue; // the caller picks NP from the list length
+        // every entry is read by the 32 lanes at once: 32 different banks
+        for (uint16_t e : list) {
+            std::set<uint32_t> banks;
+            for (uint32_t l = 0; l < 32; l++)
+                banks.insert(((sliced_lane_base(l) + e) / 4) % 32);
+            CHECK(banks.size() == 32);
+        }
+        const uint32_t m = static_cast<uint32_t>(rng() % (pq + 2));
+        for (uint32_t l = 0; l < 32; l++) {
+            SlicedCount<NP> cnt;
+            const size_t base = sliced_lane_base(l);
+            for (size_t g = 0; g < list.size(); g += 8) {
+                uint32_t x[8];
+                for (int i = 0; i < 8; i++)
+                    x[i] = rd32(tile, base + list[g + i]);
+                cnt.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            }
+            uint32_t want_ge = 0;
+            for (uint32_t r = 0; r < 32; r++) {
+                uint32_t common = 0;
+                for (int w = 0; w < 32; w++)
+                    common += __builtin_popcount(q[w] & rows[(l * 32 + r) * 32 + w]);
+                CHECK(cnt.column(r) == common);
+                if (common >= m)
+                    want_ge |= 1u << r;
+            }
+            if (m < (1u << (3 + NP)))
+                CHECK(cnt.at_least(m) == want_ge);
+        }
+    }
+}
+
+int main()
+{
+    std::mt19937 rng(12345);
+    // ---- transpose32
+    {
+        uint32_t a[32], b[32];
+        for (int i = 0; i < 32; i++)
+            a[i] = b[i] = rng();
+        transpose32(b);
+        for (int r = 0; r < 32; r++)
+            for (int c = 0; c < 32; c++)
+                CHECK(((b[c] >> r) & 1u) == ((a[r] >> c) & 1u));
+    }
+    // ---- tile: 32 raw batches as the TMA copies leave them (32 rows x 128 B, then 32 u16 popcounts)
+    std::vector<uint8_t> tile(kSlicedTileBatches * kSlicedRegionBytes, 0xAB);
+    std::vector<uint32_t> rows(32 * 32 * 32);
+    std::bernoulli_distribution bit(1.0 / 12);
+    for (auto& w : rows) {
+        w = 0;
+        for (int b = 0; b < 32; b++)
+            w |= static_cast<uint32_t>(bit(rng)) << b;
+    }
+    for (uint32_t l = 0; l < 32; l++)
+        for (uint32_t r = 0; r < 32; r++) {
+            uint32_t pc = 0;
+            for (uint32_t w = 0; w < 32; w++) {
+                wr32(tile, l * kSlicedRegionBytes + (r * 32 + w) * 4, rows[(l * 32 + r) * 32 + w]);
+                pc += __builtin_popcount(rows[(l * 32 + r) * 32 + w]);
+            }
+            const uint16_t p16 = static_cast<uint16_t>(pc);
+            std::memcpy(&tile[l * kSlicedRegionBytes + 4096 + r * 2], &p16, 2);
+        }
+    // ---- phase A as the kernel does it: lane = word column, registers = rows, in place
+    for (uint32_t b = 0; b < 32; b++) {
+        const size_t region = b * kSlicedRegionBytes;
+        uint32_t x[32][32]; // [lane][register]
+        for (uint32_t lane = 0; lane < 32; lane++)
+            for (uint32_t r = 0; r < 32; r++)
+                x[lane][r] = rd32(tile, region + (r * 32 + lane) * 4);
+        // (all reads happen before any write: __syncwarp in the kernel)
+        for (uint32_t lane = 0; lane < 32; lane++)
+            transpose32(x[lane]);
+        const size_t tbase = sliced_lane_base(b);
+        CHECK(tbase >= region && tbase + 1025 * 4 <= region + kSlicedRegionBytes);
+        for (uint32_t bb = 0; bb < 32; bb++) {
+            std::set<uint32_t> banks;
+            for (uint32_t lane = 0; lane < 32; lane++) {
+                const uint32_t idx = sliced_word_index(lane * 32 + bb);
+                CHECK(idx == lane * 32 + ((bb + lane) & 31));
+                banks.insert(((tbase / 4) + idx) % 32);
+                wr32(tile, tbase + idx * 4, x[lane][bb]);
+            }
+            CHECK(banks.size() == 32); // conflict-free stores
+        }
+        wr32(tile, tbase + sliced_word_index(kSlicedZeroPos) * 4, 0u);
+    }
+    CHECK(sliced_word_index(kSlicedZeroPos) == 1024);
+    // the word index is a bijection on [0, 1024]
+    {
+        std::set<uint32_t> seen;
+        for (uint32_t pos = 0; pos <= 1024; pos++)
+            seen.insert(sliced_word_index(pos));
+        CHECK(seen.size() == 1025 && *seen.rbegin() == 1024);
+    }
+    // ---- phase B: sparse queries on the small counter, dense ones on the large counter
+    run_queries<4>(tile, rows, rng, 40, 1.0 / 30);
+    run_queries<4>(tile, rows, rng, 10, 1.0 / 10);
+    run_queries<8>(tile, rows, rng, 10, 0.5);
+    run_queries<8>(tile, rows, rng, 3, 1.0);
+    run_queries<8>(tile, rows, rng, 3, 0.0);
+    // ---- filter bound: smallest count whose best-case score reaches ts
+    {
+        auto div = [](uint32_t c, uint32_t u) { return u ? static_cast<float>(c) / static_cast<float>(u) : 0.0f / 0.0f; };
+        for (uint32_t pq = 0; pq <= 1024; pq += (pq < 80 ? 1 : 37)) {
+            for (uint32_t u = 1; u <= 2048; u += (u < 100 ? 1 : 53))
+                for (uint32_t c = 0; c <= u; c += (u < 100 ? 1 : 7)) {
+                    const float ts = static_cast<float>(c) / static_cast<float>(u);
+                    uint32_t want = 0;
+                    if (ts > 0.0f) {
+                        if (pq == 0)
+                            want = 1;
+                        else
+                            while (want <= pq && !(div(want, pq) >= ts))
+                                want++;
+                    }
+                    CHECK(sliced_filter_min(ts, pq, div) == want);
+                }
+            CHECK(sliced_filter_min(0.0f, pq, div) == 0);
+            const float nan = 0.0f / 0.0f;
+            CHECK(sliced_filter_min(nan, pq, div) == 0);
+        }
+    }
+    if (g_fail) {
+        std::fprintf(stderr, "%d check(s) failed\n", g_fail);
+        return 1;
+    }
+    std::printf("sliced math ok\n");
+    return 0;
+}

@@ -318,6 +318,85 @@ def test_multi_query_kernel(bits, n_queries, k):
             assert_same(got, OC.c_search(qs[j], rows_np, k, cutoff), f"batch query {j} cutoff {cutoff}")
 
 
+def _sliced_queries(rows_np, seed, n_random):
+    """Query mix for the bit-sliced kernel: sparse rows, the template, an empty query, an all-ones
+    query, half-dense random queries (long lists, 8 extra counter planes)."""
+    rng = np.random.default_rng(seed)
+    n = rows_np.shape[0]
+    qs = [O.synth_template(seed, 32), np.zeros(32, np.int32), np.full(32, -1, np.int32),
+          rng.integers(-2**31, 2**31, 32).astype(np.int32), rows_np[0], rows_np[n - 1]]
+    qs += [rows_np[i] for i in rng.integers(0, n, n_random)]
+    return np.stack(qs)
+
+
+@pytest.mark.parametrize("n_rows", [1, 33, 1024, 1025, 37889, 300001])
+def test_sliced_kernel_sizes_and_ragged_tiles(monkeypatch, n_rows):
+    """Bit-sliced multi-query kernel (gsb_sliced.cuh) forced on: ragged last batch and last tile,
+    k above and below the row count, cutoffs that follow the threshold (<= 0) and the cutoff (> 0)."""
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    rows_np = OC.c_synth_db(77 + n_rows, n_rows, 32, 53)
+    db = make_db(rows_np)
+    qs = _sliced_queries(rows_np, 77 + n_rows, 14)
+    for k in (1, 10, 100):
+        for cutoff in (0.0, -1.0, 0.08, 0.3, 0.6, 1.5):
+            res = db.search_batch_rows(qs, k, cutoff)
+            for j, got in enumerate(res):
+                assert_same(got, OC.c_search(qs[j], rows_np, k, cutoff), f"sliced n={n_rows} q{j} k={k} c={cutoff}")
+
+
+@pytest.mark.parametrize("n_queries,k,grid", [(37, 100, 0), (300, 100, 0), (1030, 10, 0), (40, 512, 0), (64, 100, 8)])
+def test_sliced_kernel_ties_blocks_and_groups(monkeypatch, n_queries, k, grid):
+    """Tie groups, empty rows, more than 1024 queries (two passes), k = 512, and with GSB_GRID=8 a
+    grid small enough that the sample pass (threshold seeding) runs at this size."""
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    if grid:
+        monkeypatch.setenv("GSB_GRID", str(grid))
+    rows_np = OC.c_synth_db(900 + n_queries, 700_000, 32, 97)
+    rows_np[1000:1100] = rows_np[5]                                 # a tie group
+    rows_np[2000:2050] = 0                                          # empty fingerprints
+    rows_np[650_000:650_600] = rows_np[7]                           # a tie group larger than k
+    db = make_db(rows_np)
+    qs = _sliced_queries(rows_np, n_queries, n_queries - 6)
+    qs[6], qs[7] = rows_np[5], rows_np[7]
+    step = max(1, n_queries // 40)                                  # oracle-check a spread of the queries
+    for cutoff in (0.0, 0.4):
+        res = db.search_batch_rows(qs, k, cutoff)
+        assert len(res) == n_queries
+        for j in list(range(0, n_queries, step)) + [n_queries - 1]:
+            assert_same(res[j], OC.c_search(qs[j], rows_np, k, cutoff), f"sliced query {j} cutoff {cutoff}")
+
+
+def test_sliced_kernel_dense_queries_span_list_blocks(monkeypatch):
+    """96 half-dense queries: ~49 k list entries, three shared-memory list blocks per tile."""
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    rows_np = OC.c_synth_db(31, 150_000, 32, 61)
+    db = make_db(rows_np)
+    rng = np.random.default_rng(31)
+    qs = rng.integers(-2**31, 2**31, (96, 32)).astype(np.int32)
+    qs[10] = rows_np[99]
+    res = db.search_batch_rows(qs, 50, 0.0)
+    for j in range(0, 96, 5):
+        assert_same(res[j], OC.c_search(qs[j], rows_np, 50, 0.0), f"dense query {j}")
+
+
+def test_sliced_kernel_sample_pass_full_grid(monkeypatch):
+    """3 M rows: enough tiles for the sample pass with one CTA per SM; with and without it, and
+    against the POPC multi-query kernel."""
+    rows_np = OC.c_synth_db(8, 3_000_000, 32, 1500)
+    db = make_db(rows_np)
+    qs = _sliced_queries(rows_np, 8, 26)
+    results = {}
+    for name, kernel, sample in (("sliced+sample", "3", "1"), ("sliced", "3", "0"), ("popc", "2", "1")):
+        monkeypatch.setenv("GSB_BATCH_KERNEL", kernel)
+        monkeypatch.setenv("GSB_SLICED_SAMPLE", sample)
+        results[name] = db.search_batch_rows(qs, 100, 0.0)
+    for j in range(len(qs)):
+        assert_same(results["sliced+sample"][j], results["popc"][j], f"sample vs popc, query {j}")
+        assert_same(results["sliced"][j], results["popc"][j], f"no sample vs popc, query {j}")
+    for j in (0, 1, 2, 3, 9):
+        assert_same(results["sliced+sample"][j], OC.c_search(qs[j], rows_np, 100, 0.0), f"oracle, query {j}")
+
+
 def test_multi_query_matches_single_query_path(monkeypatch):
     rows_np = OC.c_synth_db(4, 500_000, 32, 211)
     db = make_db(rows_np)

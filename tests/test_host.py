@@ -116,3 +116,15 @@ def test_multi_chunk_host_storage():
     assert list(got_rows) == list(want_rows) and list(f32bits(got_scores)) == list(f32bits(want_scores))
     with pytest.raises(gsb.GsbError):
         db.getFingerprint(1000)
+
+
+def test_sliced_kernel_math_on_cpu():
+    """tests/cpp/test_sliced_math.cpp: one warp of the bit-sliced multi-query kernel emulated with
+    the kernel's own integer helpers (tile layout, in-place transposition, bank-conflict freedom,
+    carry-save counts, bit-sliced compare, filter bound) against plain popcounts."""
+    import subprocess
+    from conftest import ROOT
+    subprocess.run(["make", "-C", ROOT, "tests/cpp/test_sliced_math"], check=True, capture_output=True)
+    res = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_sliced_math")], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0 and "sliced math ok" in res.stdout, res.stdout + res.stderr

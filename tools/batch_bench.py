@@ -1,42 +1,55 @@
-"""Throughput of the multi-query kernel vs looping single queries.  usage: batch_bench.py [rows] [nq] [k]"""
-import os, sys, time
+"""Throughput of the multi-query kernels (bit-sliced and POPC) vs looping single queries.
+usage: batch_bench.py [rows] [nq] [k]"""
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import ctypes as C
 import numpy as np, torch
 import gpusimilarity_b200 as gsb
 from gpusimilarity_b200._lib import check, lib
-from oracle import oracle as O
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
-nq = int(sys.argv[2]) if len(sys.argv) > 2 else 256
+nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 dev = torch.device("cuda", 0)
 db = gsb.FingerprintDB.synthetic(rows, device=0, seed=0x5EED5EED, plant_period=max(64, rows // 4000))
 qrows = np.linspace(0, rows - 1, nq).astype(np.int64)
 qs = np.stack([db.getFingerprint(int(r)) for r in qrows])
+print(f"mean set bits per query: {np.unpackbits(qs.view(np.uint8)).sum() / nq:.1f}")
 d_q = torch.from_numpy(qs.copy()).to(dev)
 keys = torch.zeros(nq * K, dtype=torch.int64, device=dev)
 cnt = torch.zeros(nq, dtype=torch.int32, device=dev)
 surv = torch.zeros(nq, dtype=torch.int64, device=dev)
 st = torch.cuda.current_stream()
-def run():
-    check(lib().gsb_db_search_batch_device(db._h, st.cuda_stream, d_q.data_ptr(), nq, K, 0.0, keys.data_ptr(),
-                                           cnt.data_ptr(), surv.data_ptr()))
-run(); torch.cuda.synchronize()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record(); run(); b.record(); b.synchronize()
-ms = a.elapsed_time(b)
-print(f"batch kernel: rows={rows} nq={nq} k={K}: {ms:.2f} ms -> {nq / ms * 1e3:.1f} q/s, "
-      f"{rows * nq / ms / 1e6:.1f} G row*query/s, DB bytes amortised {rows * 128 / ms / 1e6:.0f} GB/s")
+
+
+def run(group):
+    for q0 in range(0, nq, group):
+        n = min(group, nq - q0)
+        check(lib().gsb_db_search_batch_device(db._h, st.cuda_stream, d_q[q0:].data_ptr(), n, K, 0.0,
+                                               keys[q0 * K:].data_ptr(), cnt[q0:].data_ptr(), surv[q0:].data_ptr()))
+
+
+results = {}
+for name, mode, sample, group in (("bit-sliced", "3", "1", 1024), ("bit-sliced, no sample pass", "3", "0", 1024),
+                                  ("popc", "2", "1", 256)):
+    os.environ["GSB_BATCH_KERNEL"], os.environ["GSB_SLICED_SAMPLE"] = mode, sample
+    run(group); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); run(group); b.record(); b.synchronize()
+    ms = a.elapsed_time(b)
+    results[name] = keys.cpu().numpy().astype(np.uint64).copy()
+    print(f"{name}: rows={rows} nq={nq} k={K}: {ms:.2f} ms -> {nq / ms * 1e3:.1f} q/s, "
+          f"{rows * nq / ms / 1e6:.1f} G row*query/s")
+print("bit-sliced == popc:", bool(np.array_equal(results["bit-sliced"], results["popc"])),
+      "; without sample pass == popc:", bool(np.array_equal(results["bit-sliced, no sample pass"], results["popc"])))
 rec = torch.zeros(K + 2, dtype=torch.int64, device=dev)
 nloop = min(nq, 16)
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 torch.cuda.synchronize(); a.record()
 for j in range(nloop):
     db.search_device(st.cuda_stream, d_q[j].data_ptr(), K, 0.0, rec.data_ptr(), rec.data_ptr() + 8 * (K + 1), rec.data_ptr() + 8 * K)
 b.record(); b.synchronize()
 ms1 = a.elapsed_time(b) / nloop
-print(f"single-query kernel: {ms1:.3f} ms/query -> {1e3 / ms1:.1f} q/s; batch speed-up {ms1 * nq / ms:.2f}x")
-# spot check
-k0 = keys[:K].cpu().numpy().astype(np.uint64)
+print(f"single-query kernel: {ms1:.3f} ms/query -> {1e3 / ms1:.1f} q/s")
 db.search_device(st.cuda_stream, d_q[0].data_ptr(), K, 0.0, rec.data_ptr(), rec.data_ptr() + 8 * (K + 1), rec.data_ptr() + 8 * K)
 torch.cuda.synchronize()
-print("query 0 identical:", bool(np.array_equal(k0, rec[:K].cpu().numpy().astype(np.uint64))))
+print("query 0 identical to the single-query kernel:",
+      bool(np.array_equal(results["bit-sliced"][:K], rec[:K].cpu().numpy().astype(np.uint64))))

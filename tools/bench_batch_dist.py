@@ -27,7 +27,7 @@ qs = O.synth_rows(0x5EED5EED, seed_rows, 32, 250000)          # copies of databa
 d_q = torch.from_numpy(np.ascontiguousarray(qs)).to(dev)
 s = ShardedBatchSearcher(db, args.k, local, dist, world)
 stream = torch.cuda.current_stream()
-G = ShardedBatchSearcher.MAX_QUERIES
+G = s.max_queries(args.queries, 0.0)
 def run_all():
     for q0 in range(0, args.queries, G):
         nq = min(G, args.queries - q0)
