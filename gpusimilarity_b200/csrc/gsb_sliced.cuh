@@ -13,11 +13,11 @@
 //     T_l[pos] (conflict free by construction, gsb_sliced_math.h) and adds it into bit-sliced
 //     counters with carry-save adders; after the list the counter columns are the common-bit
 //     counts of 32 x 32 rows;
-//   * a row can only beat the query's running threshold tau if common >= m, the smallest count
-//     with common/popc(q) >= tau (the union is at least popc(q)) — one bit-sliced compare; only
-//     the rare rows that pass are scored exactly (tanimoto_div, popcount trailer) and appended to
-//     the query's candidate list, with the same key, cutoff and survivor rules as the other
-//     kernels.  Select rounds, per-CTA lists and the grid-wide merge are shared with
+//   * a row can only beat the query's running threshold tau if common >= m, where m follows from
+//     score <= common / (popc(q) + pd_min - common) with pd_min the smallest row popcount of the
+//     lane's batch — one bit-sliced compare; only the rare rows that pass are scored exactly
+//     (tanimoto_div, popcount trailer) and appended to the query's candidate list, with the same
+//     key, cutoff and survivor rules as the other kernels.  Select rounds, per-CTA lists and the grid-wide merge are shared with
 //     scan_batch_kernel (batch_select_round / batch_finish).
 //
 // The host (gsb_api.cu) first runs the kernel over a strided ~1.5 % sample of the tiles to get a
@@ -34,7 +34,7 @@ namespace gsb
 constexpr uint32_t kMaxSlicedQueries = 1024;
 constexpr uint32_t kSlicedListEntries = 20480; // u16 list entries of one query block in shared memory
 constexpr uint32_t kSlicedTileBytes = kSlicedTileBatches * kSlicedRegionBytes;
-constexpr uint32_t kSlicedPerQueryBytes = 8 + 8 + 4 + 4 + 2 + 2 + 2;
+constexpr uint32_t kSlicedPerQueryBytes = 8 + 8 + 4 + 4 + 4 + 2 + 2 + 2;
 
 // Query blocks: consecutive queries whose lists fit the shared-memory list area together.
 struct SlicedMeta {
@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     __shared__ unsigned long long s_stage_tau;
     __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_next_q, s_need_select;
     __shared__ unsigned int s_claim[2];
+    __shared__ float s_pdmin[kSlicedTileBatches]; // smallest row popcount of each batch of the tile
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t nq = p.nq, nqp = (nq + 7u) & ~7u;
@@ -150,6 +151,8 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(cursor);               // [nq] list fill
     cursor += (size_t) nqp * 4;
     uint32_t* s_lofs = reinterpret_cast<uint32_t*>(cursor);                      // [nq]
+    cursor += (size_t) nqp * 4;
+    float* s_tq = reinterpret_cast<float*>(cursor);                              // [nq] filter: see sliced_tq
     cursor += (size_t) nqp * 4;
     uint16_t* s_m = reinterpret_cast<uint16_t*>(cursor);                         // [nq] filter: common >= m
     cursor += (size_t) nqp * 2;
@@ -169,10 +172,11 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     const bool drop_zero = p.cutoff > 0.0f; // reference .cu:265
     // With a cutoff every row at or above it must be seen (survivor count), so the filter follows
     // the cutoff; without one it follows the query's threshold.
-    auto filter_min = [&](uint32_t j) -> uint16_t {
+    auto update_filter = [&](uint32_t j) {
         const float ts = drop_zero ? p.cutoff : __uint_as_float(static_cast<uint32_t>((s_tau[j] + 1ull) >> 32));
         const uint32_t m = sliced_filter_min(ts, s_popq[j], [](uint32_t c, uint32_t u) { return tanimoto_div(c, u); });
-        return static_cast<uint16_t>(m > 0xffffu ? 0xffffu : m);
+        s_m[j] = static_cast<uint16_t>(m > 0xffffu ? 0xffffu : m);
+        s_tq[j] = sliced_tq(ts);
     };
 
     for (uint32_t j = tid; j < nq; j += NT) {
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     }
     __syncthreads();
     for (uint32_t j = tid; j < nq; j += NT)
-        s_m[j] = filter_min(j);
+        update_filter(j);
     const uint32_t n_blocks = sp.meta->n_blocks;
     auto load_lists = [&](uint32_t blk) { // all threads; the caller syncs
         const uint32_t q0 = sp.meta->blk_start[blk], q1 = sp.meta->blk_start[blk + 1];
@@ -214,11 +218,13 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     uint32_t phase = 0;
 
     // One query against the 1024 rows of the tile; NP = counter planes above "fours".
-    auto run_query = [&](auto np_tag, uint32_t j, uint32_t list_base, uint32_t b0, uint32_t nb_tile) {
+    auto run_query = [&](auto np_tag, uint32_t j, uint32_t list_base, uint32_t b0, uint32_t nb_tile, float pdmin) {
         constexpr int NP = decltype(np_tag)::value;
         const uint32_t pq = s_popq[j], m = s_m[j];
         if (m > pq)
             return; // no row can reach this query's threshold any more
+        // this lane's bound: its batch has no row with fewer than pdmin set bits
+        const uint32_t ml = max(m, sliced_lane_min(s_tq[j], static_cast<float>(pq) + pdmin));
         const uint32_t ng = s_ngrp[j];
         const uint4* lp = reinterpret_cast<const uint4*>(s_list + (s_lofs[j] - list_base));
         SlicedCount<NP> cnt;
@@ -235,9 +241,9 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             const uint32_t x7 = *reinterpret_cast<const uint32_t*>(my_T + (e.w >> 16));
             cnt.add8(x0, x1, x2, x3, x4, x5, x6, x7);
         }
-        uint32_t ge = m == 0 ? kFull : cnt.at_least(m);
-        if (lane >= nb_tile)
-            ge = 0; // ragged last tile: this lane has no batch
+        uint32_t ge = cnt.at_least_lane(ml);
+        if (lane >= nb_tile || (ml >> (3 + NP)) != 0)
+            ge = 0; // ragged last tile: this lane has no batch; or a bound no count of this width reaches
         unsigned hit = __ballot_sync(kFull, ge != 0);
         // exact path, one batch with candidates at a time: lane r takes row r of that batch
         while (hit) {
@@ -316,6 +322,9 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                 for (int r = 0; r < 32; r++)
                     x[r] = raw[r * 32 + lane];
                 const uint16_t pd = reinterpret_cast<const uint16_t*>(region + (size_t) kBatchRows * 128)[lane];
+                const uint32_t pd_lo = __reduce_min_sync(kFull, static_cast<uint32_t>(pd));
+                if (lane == 0)
+                    s_pdmin[b] = static_cast<float>(pd_lo);
                 __syncwarp(); // in place: every lane has read the batch before anyone overwrites it
                 transpose32(x);
                 uint32_t* T = reinterpret_cast<uint32_t*>(tile + sliced_lane_base(b));
@@ -329,6 +338,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         }
         cta_sync<NT>();
         // ---- phase B: warps take queries one at a time
+        const float my_pdmin = s_pdmin[lane];
         for (uint32_t blk = 0; blk < n_blocks; blk++) {
             if (blk > 0) {
                 cta_sync<NT>(); // every warp has left the previous block
@@ -347,16 +357,16 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                 if (j >= q_end)
                     break;
                 if (s_ngrp[j] <= 15) // <= 120 set bits: counts fit 7 planes
-                    run_query(std::integral_constant<int, 4>{}, j, list_base, b0, nb_tile);
+                    run_query(std::integral_constant<int, 4>{}, j, list_base, b0, nb_tile, my_pdmin);
                 else
-                    run_query(std::integral_constant<int, 8>{}, j, list_base, b0, nb_tile);
+                    run_query(std::integral_constant<int, 8>{}, j, list_base, b0, nb_tile, my_pdmin);
             }
         }
         cta_sync<NT>();
         // ---- lists that passed 1024 entries are cut back (staged through the tile buffer)
         if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
             batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, tid,
-                                   [&](uint32_t j) { s_m[j] = filter_min(j); });
+                                   [&](uint32_t j) { update_filter(j); });
             if (tid == 0)
                 s_need_select = 0;
         }

@@ -132,6 +132,19 @@ GSB_UNROLL
         }
         return gt | eq;
     }
+    // the same with a different m in every lane (no branches on m)
+    GSB_HD uint32_t at_least_lane(uint32_t m) const
+    {
+        uint32_t gt = 0, eq = ~0u;
+GSB_UNROLL
+        for (int p = 3 + NP - 1; p >= 0; p--) {
+            const uint32_t c = plane(p);
+            const uint32_t mb = 0u - ((m >> p) & 1u); // all ones where m has bit p
+            gt |= eq & c & ~mb;
+            eq &= ~(c ^ mb);
+        }
+        return gt | eq;
+    }
     // count of column r
     GSB_HD uint32_t column(uint32_t r) const
     {
@@ -160,6 +173,25 @@ template <class Div> GSB_HD uint32_t sliced_filter_min(float ts, uint32_t pq, Di
     while (m <= pq && !(div(m, pq) >= ts))
         m++;
     return m;
+}
+
+// Tighter, per-batch bound: every row of a batch has at least pd_min set bits, the union is
+// pq + pd - common, so score >= ts needs common >= ts/(1+ts) * (pq + pd_min).  sliced_tq() is that
+// factor rounded DOWN (by far more than the rounding of the score and of this arithmetic), and
+// sliced_lane_min() the resulting count, never above the exact bound.
+GSB_HD float sliced_tq(float ts)
+{
+    if (!(ts > 0.0f))
+        return 0.0f;
+    return ts / (1.0f + ts) * (1.0f - 1.0f / 1048576.0f);
+}
+GSB_HD uint32_t sliced_lane_min(float tq, float pq_plus_pdmin)
+{
+    const float x = tq * pq_plus_pdmin - 0.001f; // the product is off by < 2^-13 for sums up to 2048
+    if (!(x > 0.0f))
+        return 0u;
+    const uint32_t f = static_cast<uint32_t>(x);
+    return static_cast<float>(f) < x ? f + 1u : f; // ceil
 }
 
 } // namespace gsb

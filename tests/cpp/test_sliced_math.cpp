@@ -81,8 +81,10 @@ static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint
                 if (common >= m)
                     want_ge |= 1u << r;
             }
-            if (m < (1u << (3 + NP)))
+            if (m < (1u << (3 + NP))) {
                 CHECK(cnt.at_least(m) == want_ge);
+                CHECK(cnt.at_least_lane(m) == want_ge);
+            }
         }
     }
 }
@@ -178,6 +180,33 @@ int main()
             const float nan = 0.0f / 0.0f;
             CHECK(sliced_filter_min(nan, pq, div) == 0);
         }
+    }
+    // ---- per-batch bound: a row that reaches ts is never below sliced_lane_min, for any pd_min <= pd,
+    // including the equality case ts == the row's own score; and the bound is not sloppy
+    {
+        uint64_t loose = 0, total = 0;
+        for (uint32_t pq = 1; pq <= 1024; pq += (pq < 70 ? 1 : 61))
+            for (uint32_t pd = 0; pd <= 1024; pd += (pd < 70 ? 1 : 67))
+                for (uint32_t c = 0; c <= (pq < pd ? pq : pd); c += (c < 40 ? 1 : 13)) {
+                    const uint32_t u = pq + pd - c;
+                    if (u == 0)
+                        continue;
+                    const float ts = static_cast<float>(c) / static_cast<float>(u);
+                    const float tq = sliced_tq(ts);
+                    for (uint32_t pdmin = pd > 3 ? pd - 3 : 0; pdmin <= pd; pdmin++) {
+                        const uint32_t m = sliced_lane_min(tq, static_cast<float>(pq + pdmin));
+                        CHECK(m <= c);
+                        if (pdmin == pd) {
+                            total++;
+                            loose += (m + 1 < c);
+                        }
+                    }
+                    // a slightly lower threshold keeps the row, a slightly higher one may drop it
+                    CHECK(sliced_lane_min(sliced_tq(ts * 0.999f), static_cast<float>(pq + pd)) <= c);
+                }
+        CHECK(loose == 0); // with the true popcount the bound is within one count of exact
+        CHECK(sliced_lane_min(sliced_tq(0.0f), 100.0f) == 0 && sliced_lane_min(sliced_tq(-1.0f), 100.0f) == 0);
+        (void) total;
     }
     if (g_fail) {
         std::fprintf(stderr, "%d check(s) failed\n", g_fail);
