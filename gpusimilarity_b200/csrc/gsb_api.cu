@@ -134,7 +134,8 @@ struct Workspace {
     uint16_t* sngrp = nullptr;
     uint16_t* spopq = nullptr;
     gsb::SlicedMeta* smeta = nullptr;
-    unsigned long long* stau = nullptr;    // [kMaxSlicedQueries] thresholds from the sample pass
+    unsigned long long* stau = nullptr;    // [kMaxSlicedQueries] thresholds shared by the CTAs of a pass
+    unsigned int* shist = nullptr;         // [kMaxSlicedQueries][kSlicedHistBuckets] candidate score histograms
     unsigned long long* ssample = nullptr; // [bnq_cap][bk_cap + 2] sample pass results
 };
 
@@ -367,6 +368,7 @@ void ws_free(Shard& sh)
     cudaFree(ws.sngrp);
     cudaFree(ws.spopq);
     cudaFree(ws.stau);
+    cudaFree(ws.shist);
     cudaFree(ws.smeta);
     if (ws.bout_host)
         cudaFreeHost(ws.bout_host);
@@ -770,6 +772,7 @@ int sliced_reserve(Shard& sh)
     GSB_CUDA(cudaMalloc(&ws.sngrp, nq * sizeof(uint16_t)));
     GSB_CUDA(cudaMalloc(&ws.spopq, nq * sizeof(uint16_t)));
     GSB_CUDA(cudaMalloc(&ws.stau, nq * sizeof(unsigned long long)));
+    GSB_CUDA(cudaMalloc(&ws.shist, nq * gsb::kSlicedHistBuckets * sizeof(unsigned int)));
     GSB_CUDA(cudaMalloc(&ws.smeta, sizeof(gsb::SlicedMeta)));
     return GSB_OK;
 }
@@ -874,26 +877,33 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     sp.ngrp = ws.sngrp;
     sp.popq = ws.spopq;
     sp.meta = ws.smeta;
-    auto launch = [&]() -> int {
+    sp.ghist = ws.shist;
+    sp.gtau = ws.stau;
+    // a pass: claims [0, n_mini) are each CTA's warm-up mini tile, then the tiles themselves
+    auto launch = [&](uint32_t tiles, uint32_t step) -> int {
+        GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));
+        sp.n_mini = std::min<uint32_t>(static_cast<uint32_t>(grid), tiles);
+        sp.n_claims = sp.n_mini + tiles;
+        sp.tile_step = step;
         void* args[] = {&sp};
         GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_sliced_kernel<kWarps>), dim3(grid),
                                              dim3(kWarps * 32), args, smem, st));
         g_launches++;
         return GSB_OK;
     };
-    // ---- sample pass: every step-th tile, ~1.5 % of the shard but at least 4 tiles per CTA; its
-    // k-th key per query (minus one, so that the key itself stays eligible) seeds the full pass
+    GSB_CUDA(cudaMemsetAsync(ws.stau, 0, static_cast<size_t>(nq) * sizeof(unsigned long long), st));
+    // ---- optional sample pass (GSB_SLICED_SAMPLE=1): every step-th tile, ~1.5 % of the shard but at
+    // least 4 tiles per CTA; its k-th key per query (minus one, so that the key itself stays
+    // eligible) seeds the full pass.  Off by default: the CTAs of one pass already share their
+    // thresholds through the grid-wide score histograms.
     const uint32_t sample_claims = std::max<uint32_t>(4u * grid, n_tiles / 64u);
-    const bool sample = env_int("GSB_SLICED_SAMPLE", 1) != 0 && static_cast<uint64_t>(sample_claims) * 4u <= n_tiles;
+    const bool sample = env_int("GSB_SLICED_SAMPLE", 0) != 0 && static_cast<uint64_t>(sample_claims) * 4u <= n_tiles;
     if (sample) {
         unsigned long long* skeys = ws.ssample;
         unsigned long long* ssurv = skeys + static_cast<size_t>(nq) * k;
         uint32_t* scnt = reinterpret_cast<uint32_t*>(ssurv + nq);
         fill_batch_params(db, sh, nq, k, cutoff, d_queries, skeys, scnt, ssurv, &sp.b);
-        sp.tau_init = nullptr;
-        sp.n_claims = sample_claims;
-        sp.tile_step = n_tiles / sample_claims;
-        rc = launch();
+        rc = launch(sample_claims, n_tiles / sample_claims);
         if (rc)
             return rc;
         gsb::sliced_seed_tau_kernel<<<(nq + 255) / 256, 256, 0, st>>>(skeys, scnt, nq, k, ws.stau);
@@ -901,10 +911,7 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         GSB_CUDA(cudaGetLastError());
     }
     fill_batch_params(db, sh, nq, k, cutoff, d_queries, out_keys, out_n, out_surv, &sp.b);
-    sp.tau_init = sample ? ws.stau : nullptr;
-    sp.n_claims = n_tiles;
-    sp.tile_step = 1;
-    return launch();
+    return launch(n_tiles, 1);
 }
 
 // One pass over one shard for nq <= batch_max_queries(which) queries already in device memory.

@@ -48,16 +48,16 @@ struct BatchParams {
 
 // Cut back every candidate list of this CTA that is more than half full (or, with exact_all, cut
 // every list to its exact sorted top k).  All NT threads; lists are staged through cs.buf.
-// tau_raised(j) runs on thread 0 after s_tau[j] went up.
-template <int NT, class F>
+// tau_raised(j) runs on thread 0 after s_tau[j] went up; lists with skip(j) are left alone.
+template <int NT, class F, class S>
 __device__ void batch_select_round(const CandShared& cs, unsigned long long* my_cand, unsigned int* s_cnt,
                                    unsigned long long* s_tau, uint32_t nq, uint32_t k, bool exact_all, uint32_t tid,
-                                   F tau_raised)
+                                   F tau_raised, S skip)
 {
     cta_sync<NT>();
     for (uint32_t j = 0; j < nq; j++) {
         const uint32_t n = s_cnt[j] < kBatchListCap ? s_cnt[j] : kBatchListCap;
-        if (!exact_all && n <= kBatchListCap / 2)
+        if ((!exact_all && n <= kBatchListCap / 2) || skip(j))
             continue;
         unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
         for (uint32_t i = tid; i < n; i += NT)
@@ -83,16 +83,17 @@ __device__ void batch_select_round(const CandShared& cs, unsigned long long* my_
 
 // End of a multi-query launch, all NT threads of every CTA: exact sorted top-k of every list to
 // global memory, grid-wide arrival (cooperative launch: all CTAs resident), per-query merges
-// spread over the CTAs, and the last CTA leaves the control block clean.
-template <int NT>
+// spread over the CTAs, and the last CTA leaves the control block clean.  Lists with sorted(j) are
+// already exact and sorted.
+template <int NT, class S>
 __device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigned long long* my_cand,
                              unsigned int* s_cnt, unsigned long long* s_tau, const unsigned long long* s_surv,
-                             unsigned int* s_alive, uint32_t tid)
+                             unsigned int* s_alive, uint32_t tid, S sorted)
 {
     const uint32_t nq = p.nq;
     const bool drop_zero = p.cutoff > 0.0f;
     __threadfence_block();
-    batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, true, tid, [](uint32_t) {});
+    batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, true, tid, [](uint32_t) {}, sorted);
     for (uint32_t j = 0; j < nq; j++) {
         const uint32_t n = s_cnt[j];
         const unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
@@ -257,7 +258,8 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     __syncthreads();
 
     auto select_round = [&]() {
-        batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, tid, [](uint32_t) {});
+        batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, tid, [](uint32_t) {},
+                               [](uint32_t) { return false; });
     };
 
     const bool drop_zero = p.cutoff > 0.0f;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
             break;
         }
     }
-    batch_finish<NT>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, tid);
+    batch_finish<NT>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, tid, [](uint32_t) { return false; });
 }
 
 // Merge of all-gathered per-rank batch records: one CTA per query.  Record layout per rank:

@@ -20,9 +20,15 @@
 //     key, cutoff and survivor rules as the other kernels.  Select rounds, per-CTA lists and the grid-wide merge are shared with
 //     scan_batch_kernel (batch_select_round / batch_finish).
 //
-// The host (gsb_api.cu) first runs the kernel over a strided ~1.5 % sample of the tiles to get a
-// threshold per query, then over all tiles starting from those thresholds, so that almost no row
-// of the full pass takes the exact path.  Dense queries are just longer lists (no fallback).
+//   * thresholds are shared by the whole grid: every candidate is counted in a global score
+//     histogram of its query; between tiles each CTA turns the histograms of "its" queries into
+//     thresholds (floor of the bucket where the count from the top reaches k), publishes them,
+//     and picks up everybody else's.  After the first few tiles almost no row takes the exact
+//     path.  A CTA's first tile is a 128-row mini tile so that the warm-up (threshold 0: every
+//     row is a candidate) stays cheap.
+//
+// Dense queries are just longer lists (no fallback).  GSB_SLICED_SAMPLE=1 adds a strided ~1.5 %
+// sample pass whose k-th keys seed the full pass (useful only where CTAs cannot share thresholds).
 #pragma once
 
 #include "gsb_batch.cuh"
@@ -34,7 +40,21 @@ namespace gsb
 constexpr uint32_t kMaxSlicedQueries = 1024;
 constexpr uint32_t kSlicedListEntries = 20480; // u16 list entries of one query block in shared memory
 constexpr uint32_t kSlicedTileBytes = kSlicedTileBatches * kSlicedRegionBytes;
-constexpr uint32_t kSlicedPerQueryBytes = 8 + 8 + 4 + 4 + 4 + 2 + 2 + 2;
+constexpr uint32_t kSlicedMiniBatches = 4;     // batches of a CTA's very first (warm-up) tile
+constexpr uint32_t kSlicedPruneMin = 64;       // lists longer than this are pruned when their threshold rises
+constexpr uint32_t kSlicedWarpSortMax = 64;    // final lists up to this length are sorted by one warp
+
+// Per-query constants and filter state, one 16-byte shared-memory load per (query, tile).
+struct SlicedQuery {
+    uint32_t lofs;  // first list entry (global numbering)
+    float tq;       // filter factor, see sliced_tq
+    uint16_t m;     // filter: common >= m (batch-independent part)
+    uint16_t popq;  // query popcount
+    uint16_t ngrp;  // list length in groups of 8
+    uint16_t flags; // kSlicedDirty: tau rose since the list was last pruned; kSlicedSorted: list is final
+};
+constexpr uint16_t kSlicedDirty = 1, kSlicedSorted = 2;
+constexpr uint32_t kSlicedPerQueryBytes = 8 + 8 + 4 + sizeof(SlicedQuery);
 
 // Query blocks: consecutive queries whose lists fit the shared-memory list area together.
 struct SlicedMeta {
@@ -50,8 +70,11 @@ struct SlicedParams {
     const uint16_t* ngrp;                // [nq] groups of 8 entries
     const uint16_t* popq;                // [nq] query popcounts
     const SlicedMeta* meta;
-    const unsigned long long* tau_init;  // [nq] starting thresholds, or nullptr
-    uint32_t n_claims, tile_step;        // tiles scanned: claim c -> tile c * tile_step
+    unsigned int* ghist;                 // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
+    unsigned long long* gtau;            // [nq] thresholds shared by all CTAs; starting values on entry
+    // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c * tile_step;
+    // claim n_mini + t is tile t * tile_step (without those batches where t < n_mini)
+    uint32_t n_claims, n_mini, tile_step;
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem()
@@ -114,13 +137,31 @@ sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uin
     }
 }
 
-// Thresholds for the full pass from the sample pass: the k-th key of the sample stays eligible.
+// Thresholds for the full pass from a sample pass: the k-th key of the sample stays eligible.
 __global__ void sliced_seed_tau_kernel(const unsigned long long* keys, const uint32_t* counts, uint32_t nq, uint32_t k,
                                        unsigned long long* tau)
 {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nq)
-        tau[j] = (counts[j] >= k && k > 0 && keys[(uint64_t) j * k + k - 1] > 0) ? keys[(uint64_t) j * k + k - 1] - 1ull : 0ull;
+    if (j < nq && k > 0 && counts[j] >= k && keys[(uint64_t) j * k + k - 1] > tau[j] + 1ull)
+        tau[j] = keys[(uint64_t) j * k + k - 1] - 1ull;
+}
+
+// Descending sort of list[0, n), n <= 64, by one warp (keys are distinct: they carry the row);
+// keeps the best min(n, k).
+__device__ __forceinline__ void sliced_warp_sort(unsigned long long* list, uint32_t n, uint32_t k, uint32_t lane)
+{
+    const unsigned long long k0 = lane < n ? list[lane] : 0ull, k1 = lane + 32 < n ? list[lane + 32] : 0ull;
+    uint32_t r0 = 0, r1 = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const unsigned long long other = __shfl_sync(0xffffffffu, i < 32 ? k0 : k1, i & 31);
+        r0 += other > k0;
+        r1 += other > k1;
+    }
+    __syncwarp();
+    if (lane < n && r0 < k)
+        list[r0] = k0;
+    if (lane + 32 < n && r1 < k)
+        list[r1] = k1;
 }
 
 template <int CW>
@@ -144,21 +185,13 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     uint16_t* s_pd = reinterpret_cast<uint16_t*>(smem + kSlicedTileBytes);       // [1024] row popcounts of the tile
     uint16_t* s_list = s_pd + kSlicedTileBatches * kBatchRows;                   // [kSlicedListEntries]
     uint8_t* cursor = reinterpret_cast<uint8_t*>(s_list + kSlicedListEntries);
+    SlicedQuery* s_qc = reinterpret_cast<SlicedQuery*>(cursor);                  // [nq]
+    cursor += (size_t) nqp * sizeof(SlicedQuery);
     unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(cursor);   // [nq] keys <= tau are out
     cursor += (size_t) nqp * 8;
     unsigned long long* s_surv = reinterpret_cast<unsigned long long*>(cursor);  // [nq]
     cursor += (size_t) nqp * 8;
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(cursor);               // [nq] list fill
-    cursor += (size_t) nqp * 4;
-    uint32_t* s_lofs = reinterpret_cast<uint32_t*>(cursor);                      // [nq]
-    cursor += (size_t) nqp * 4;
-    float* s_tq = reinterpret_cast<float*>(cursor);                              // [nq] filter: see sliced_tq
-    cursor += (size_t) nqp * 4;
-    uint16_t* s_m = reinterpret_cast<uint16_t*>(cursor);                         // [nq] filter: common >= m
-    cursor += (size_t) nqp * 2;
-    uint16_t* s_popq = reinterpret_cast<uint16_t*>(cursor);
-    cursor += (size_t) nqp * 2;
-    uint16_t* s_ngrp = reinterpret_cast<uint16_t*>(cursor);
     // the select rounds run between tiles and stage through the (then dead) tile buffer
     CandShared cs;
     cs.buf = reinterpret_cast<unsigned long long*>(tile);
@@ -174,18 +207,24 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     // the cutoff; without one it follows the query's threshold.
     auto update_filter = [&](uint32_t j) {
         const float ts = drop_zero ? p.cutoff : __uint_as_float(static_cast<uint32_t>((s_tau[j] + 1ull) >> 32));
-        const uint32_t m = sliced_filter_min(ts, s_popq[j], [](uint32_t c, uint32_t u) { return tanimoto_div(c, u); });
-        s_m[j] = static_cast<uint16_t>(m > 0xffffu ? 0xffffu : m);
-        s_tq[j] = sliced_tq(ts);
+        const uint32_t m = sliced_filter_min(ts, s_qc[j].popq, [](uint32_t c, uint32_t u) { return tanimoto_div(c, u); });
+        s_qc[j].m = static_cast<uint16_t>(m > 0xffffu ? 0xffffu : m);
+        s_qc[j].tq = sliced_tq(ts);
     };
 
     for (uint32_t j = tid; j < nq; j += NT) {
-        s_tau[j] = sp.tau_init ? sp.tau_init[j] : 0ull;
+        s_tau[j] = sp.gtau[j];
         s_surv[j] = 0;
         s_cnt[j] = 0;
-        s_lofs[j] = sp.lofs[j];
-        s_popq[j] = sp.popq[j];
-        s_ngrp[j] = sp.ngrp[j];
+        SlicedQuery qc;
+        qc.lofs = sp.lofs[j];
+        qc.popq = sp.popq[j];
+        qc.ngrp = sp.ngrp[j];
+        qc.flags = 0;
+        qc.m = 0;
+        qc.tq = 0.0f;
+        s_qc[j] = qc;
+        update_filter(j);
     }
     if (tid == 0) {
         s_alive = 0;
@@ -197,14 +236,12 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         mbar_fence_init();
     }
     __syncthreads();
-    for (uint32_t j = tid; j < nq; j += NT)
-        update_filter(j);
     const uint32_t n_blocks = sp.meta->n_blocks;
     auto load_lists = [&](uint32_t blk) { // all threads; the caller syncs
         const uint32_t q0 = sp.meta->blk_start[blk], q1 = sp.meta->blk_start[blk + 1];
         if (q1 <= q0)
             return;
-        const uint32_t first = s_lofs[q0], last = s_lofs[q1 - 1] + s_ngrp[q1 - 1] * kSlicedGroup;
+        const uint32_t first = s_qc[q0].lofs, last = s_qc[q1 - 1].lofs + s_qc[q1 - 1].ngrp * kSlicedGroup;
         const uint4* src = reinterpret_cast<const uint4*>(sp.lists + first);
         uint4* dst = reinterpret_cast<uint4*>(s_list);
         for (uint32_t i = tid; i < (last - first) / 8; i += NT)
@@ -217,16 +254,14 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     const uint32_t row_base32 = static_cast<uint32_t>(p.row_base);
     uint32_t phase = 0;
 
-    // One query against the 1024 rows of the tile; NP = counter planes above "fours".
-    auto run_query = [&](auto np_tag, uint32_t j, uint32_t list_base, uint32_t b0, uint32_t nb_tile, float pdmin) {
+    // One query against the rows of the tile held by lanes [lane_lo, lane_hi); NP = counter planes
+    // above "fours".
+    auto run_query = [&](auto np_tag, uint32_t j, const SlicedQuery qc, uint32_t list_base, uint32_t b0,
+                         uint32_t lane_lo, uint32_t lane_hi, float pdmin) {
         constexpr int NP = decltype(np_tag)::value;
-        const uint32_t pq = s_popq[j], m = s_m[j];
-        if (m > pq)
-            return; // no row can reach this query's threshold any more
-        // this lane's bound: its batch has no row with fewer than pdmin set bits
-        const uint32_t ml = max(m, sliced_lane_min(s_tq[j], static_cast<float>(pq) + pdmin));
-        const uint32_t ng = s_ngrp[j];
-        const uint4* lp = reinterpret_cast<const uint4*>(s_list + (s_lofs[j] - list_base));
+        const uint32_t pq = qc.popq;
+        const uint4* lp = reinterpret_cast<const uint4*>(s_list + (qc.lofs - list_base));
+        const uint32_t ng = qc.ngrp;
         SlicedCount<NP> cnt;
 #pragma unroll 2
         for (uint32_t g = 0; g < ng; g++) {
@@ -241,9 +276,11 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             const uint32_t x7 = *reinterpret_cast<const uint32_t*>(my_T + (e.w >> 16));
             cnt.add8(x0, x1, x2, x3, x4, x5, x6, x7);
         }
+        // this lane's bound: its batch has no row with fewer than pdmin set bits
+        const uint32_t ml = max(static_cast<uint32_t>(qc.m), sliced_lane_min(qc.tq, static_cast<float>(pq) + pdmin));
         uint32_t ge = cnt.at_least_lane(ml);
-        if (lane >= nb_tile || (ml >> (3 + NP)) != 0)
-            ge = 0; // ragged last tile: this lane has no batch; or a bound no count of this width reaches
+        if (lane < lane_lo || lane >= lane_hi || (ml >> (3 + NP)) != 0)
+            ge = 0; // no batch for this lane in this tile; or a bound no count of this width reaches
         unsigned hit = __ballot_sync(kFull, ge != 0);
         // exact path, one batch with candidates at a time: lane r takes row r of that batch
         while (hit) {
@@ -283,6 +320,11 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                     if (idx >= kBatchListCap)
                         __trap(); // unreachable: lists are cut to <= 1024 entries between tiles
                     my_cand[(uint64_t) j * kBatchListCap + idx] = key;
+                    // every candidate is counted once in the grid-wide score histogram of its query
+                    const uint32_t bucket = sliced_bucket(__float_as_uint(score));
+                    const unsigned peers = __match_any_sync(pm, bucket);
+                    if (lane == static_cast<uint32_t>(__ffs(peers) - 1))
+                        atomicAdd(&sp.ghist[(uint64_t) j * kSlicedHistBuckets + bucket], static_cast<unsigned int>(__popc(peers)));
                 }
             }
         }
@@ -295,8 +337,15 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         const uint32_t claim = s_claim[it & 1];
         if (claim >= sp.n_claims)
             break;
-        const uint32_t b0 = claim * sp.tile_step * kSlicedTileBatches;
-        const uint32_t nb_tile = p.n_batches - b0 < kSlicedTileBatches ? p.n_batches - b0 : kSlicedTileBatches;
+        const bool mini = claim < sp.n_mini;
+        const uint32_t t_idx = mini ? claim : claim - sp.n_mini;
+        const uint32_t b0 = t_idx * sp.tile_step * kSlicedTileBatches;
+        uint32_t nb_tile = p.n_batches - b0 < kSlicedTileBatches ? p.n_batches - b0 : kSlicedTileBatches;
+        uint32_t lane_lo = 0;
+        if (mini)
+            nb_tile = nb_tile < kSlicedMiniBatches ? nb_tile : kSlicedMiniBatches;
+        else if (t_idx < sp.n_mini)
+            lane_lo = kSlicedMiniBatches; // those batches were this tile's mini tile
         // ---- phase A: TMA the tile in (every warp its own batches), transpose in place
         const uint32_t n_mine = warp < nb_tile ? (nb_tile - warp + CW - 1) / CW : 0u;
         if (lane == 0 && n_mine) {
@@ -348,7 +397,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                 cta_sync<NT>();
             }
             const uint32_t q_end = n_blocks == 1 ? nq : sp.meta->blk_start[blk + 1];
-            const uint32_t list_base = n_blocks == 1 ? 0u : s_lofs[sp.meta->blk_start[blk]];
+            const uint32_t list_base = n_blocks == 1 ? 0u : s_qc[sp.meta->blk_start[blk]].lofs;
             for (;;) {
                 uint32_t j = 0;
                 if (lane == 0)
@@ -356,22 +405,111 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                 j = __shfl_sync(kFull, j, 0);
                 if (j >= q_end)
                     break;
-                if (s_ngrp[j] <= 15) // <= 120 set bits: counts fit 7 planes
-                    run_query(std::integral_constant<int, 4>{}, j, list_base, b0, nb_tile, my_pdmin);
+                const SlicedQuery qc = s_qc[j];
+                if (qc.m > qc.popq)
+                    continue; // no row can reach this query's threshold any more
+                if (qc.ngrp <= 15) // <= 120 set bits: counts fit 7 planes
+                    run_query(std::integral_constant<int, 4>{}, j, qc, list_base, b0, lane_lo, nb_tile, my_pdmin);
                 else
-                    run_query(std::integral_constant<int, 8>{}, j, list_base, b0, nb_tile, my_pdmin);
+                    run_query(std::integral_constant<int, 8>{}, j, qc, list_base, b0, lane_lo, nb_tile, my_pdmin);
             }
         }
         cta_sync<NT>();
-        // ---- lists that passed 1024 entries are cut back (staged through the tile buffer)
+        // ---- between tiles: share thresholds across the grid.  This CTA turns the global score
+        // histograms of "its" queries (j = CTA, CTA + grid, ...) into thresholds: the floor of the
+        // bucket where the count of candidates from the top reaches k is a lower bound of the
+        // query's k-th best score over everything the grid has scanned so far.
+        for (uint32_t j = blockIdx.x + warp * gridDim.x; j < nq; j += CW * gridDim.x) {
+            const uint4* row = reinterpret_cast<const uint4*>(sp.ghist + (uint64_t) j * kSlicedHistBuckets) + lane * 8;
+            uint32_t c[32]; // this lane's 32 consecutive buckets
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint4 v = __ldcg(row + i);
+                c[4 * i] = v.x, c[4 * i + 1] = v.y, c[4 * i + 2] = v.z, c[4 * i + 3] = v.w;
+            }
+            uint32_t mine = 0;
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+                mine += c[i];
+            uint32_t incl = mine; // candidates in this lane's buckets and above
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t v = __shfl_down_sync(kFull, incl, d);
+                if (lane + d < 32)
+                    incl += v;
+            }
+            const unsigned reach = __ballot_sync(kFull, incl >= p.k);
+            if (reach == 0)
+                continue; // fewer than k candidates so far
+            if (lane == 31u - __clz(reach)) {
+                uint32_t acc = incl - mine, bstar = 0;
+                bool found = false;
+#pragma unroll
+                for (int i = 31; i >= 0; i--) {
+                    acc += c[i];
+                    if (!found && acc >= p.k) {
+                        found = true;
+                        bstar = lane * 32 + i;
+                    }
+                }
+                if (bstar >= 1) // candidates must beat tau strictly; the bucket floor itself stays eligible
+                    atomicMax(&sp.gtau[j], (static_cast<unsigned long long>(sliced_bucket_floor_bits(bstar)) << 32) - 1ull);
+            }
+        }
+        for (uint32_t j = tid; j < nq; j += NT) {
+            const unsigned long long t = __ldcg(&sp.gtau[j]);
+            if (t > s_tau[j]) {
+                s_tau[j] = t;
+                update_filter(j);
+                s_qc[j].flags |= kSlicedDirty;
+            }
+        }
+        cta_sync<NT>();
+        // ---- lists whose threshold rose drop the entries that fell below it (one warp per list)
+        for (uint32_t j = warp; j < nq; j += CW) {
+            const uint32_t n = s_cnt[j];
+            if (n <= kSlicedPruneMin || !(s_qc[j].flags & kSlicedDirty))
+                continue;
+            const unsigned long long tau = s_tau[j];
+            unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
+            uint32_t out = 0;
+            for (uint32_t base = 0; base < n; base += 32) {
+                const unsigned long long key = base + lane < n ? list[base + lane] : 0ull;
+                __syncwarp();
+                const bool keep = key > tau;
+                const unsigned km = __ballot_sync(kFull, keep);
+                if (keep)
+                    list[out + __popc(km & ((1u << lane) - 1u))] = key;
+                out += __popc(km);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                s_cnt[j] = out;
+                s_qc[j].flags &= static_cast<uint16_t>(~kSlicedDirty);
+            }
+        }
+        // ---- lists that still hold more than 1024 entries are cut back (staged through the tile buffer)
         if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
             batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, tid,
-                                   [&](uint32_t j) { update_filter(j); });
+                                   [&](uint32_t j) { update_filter(j); }, [](uint32_t) { return false; });
             if (tid == 0)
                 s_need_select = 0;
         }
     }
-    batch_finish<NT>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, tid);
+    // ---- final per-CTA lists: short ones are sorted by one warp each, the rest by the whole CTA
+    for (uint32_t j = warp; j < nq; j += CW) {
+        const uint32_t n = s_cnt[j];
+        if (n > kSlicedWarpSortMax)
+            continue;
+        sliced_warp_sort(my_cand + (uint64_t) j * kBatchListCap, n, p.k, lane);
+        if (lane == 0) {
+            s_cnt[j] = n < p.k ? n : p.k;
+            s_qc[j].flags |= kSlicedSorted;
+        }
+    }
+    cta_sync<NT>();
+    batch_finish<NT>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, tid,
+                     [&](uint32_t j) { return (s_qc[j].flags & kSlicedSorted) != 0; });
 }
 
 } // namespace gsb

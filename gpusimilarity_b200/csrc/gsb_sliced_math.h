@@ -132,18 +132,18 @@ GSB_UNROLL
         }
         return gt | eq;
     }
-    // the same with a different m in every lane (no branches on m)
+    // the same with a different m in every lane and no branches: borrow chain of (count - m),
+    // one three-input logic op per plane; a column is >= m iff no borrow comes out of the top
     GSB_HD uint32_t at_least_lane(uint32_t m) const
     {
-        uint32_t gt = 0, eq = ~0u;
+        uint32_t borrow = 0;
 GSB_UNROLL
-        for (int p = 3 + NP - 1; p >= 0; p--) {
+        for (int p = 0; p < 3 + NP; p++) {
             const uint32_t c = plane(p);
-            const uint32_t mb = 0u - ((m >> p) & 1u); // all ones where m has bit p
-            gt |= eq & c & ~mb;
-            eq &= ~(c ^ mb);
+            const uint32_t mb = static_cast<uint32_t>(static_cast<int32_t>(m << (31 - p)) >> 31); // bit p of m, everywhere
+            borrow = (~c & mb) | (~(c ^ mb) & borrow);
         }
-        return gt | eq;
+        return ~borrow;
     }
     // count of column r
     GSB_HD uint32_t column(uint32_t r) const
@@ -192,6 +192,22 @@ GSB_HD uint32_t sliced_lane_min(float tq, float pq_plus_pdmin)
         return 0u;
     const uint32_t f = static_cast<uint32_t>(x);
     return static_cast<float>(f) < x ? f + 1u : f; // ceil
+}
+
+// Global per-query score histogram (threshold sharing between CTAs): monotone bucket of a score's
+// float bits with 7 mantissa bits kept; everything below 2^-6 shares bucket 0, 1.0 is bucket 769.
+constexpr uint32_t kSlicedHistBuckets = 1024;
+constexpr uint32_t kSlicedHistShift = 16;
+constexpr uint32_t kSlicedHistBase = (0x3c800000u >> kSlicedHistShift) - 1u;
+GSB_HD uint32_t sliced_bucket(uint32_t score_bits)
+{
+    const uint32_t b = score_bits >> kSlicedHistShift;
+    return b > kSlicedHistBase ? (b - kSlicedHistBase < kSlicedHistBuckets ? b - kSlicedHistBase : kSlicedHistBuckets - 1u) : 0u;
+}
+// smallest score bits that fall into bucket b (b >= 1)
+GSB_HD uint32_t sliced_bucket_floor_bits(uint32_t b)
+{
+    return (b + kSlicedHistBase) << kSlicedHistShift;
 }
 
 } // namespace gsb

@@ -208,6 +208,29 @@ int main()
         CHECK(sliced_lane_min(sliced_tq(0.0f), 100.0f) == 0 && sliced_lane_min(sliced_tq(-1.0f), 100.0f) == 0);
         (void) total;
     }
+    // ---- histogram buckets: monotone in the score, floor of a bucket maps back into it
+    {
+        uint32_t prev = 0;
+        for (uint32_t u = 1; u <= 2048; u += 3)
+            for (uint32_t c = 0; c <= u; c += 1 + u / 64) {
+                const float a = static_cast<float>(c) / static_cast<float>(u);
+                uint32_t bits;
+                std::memcpy(&bits, &a, 4);
+                const uint32_t b = sliced_bucket(bits);
+                CHECK(b < kSlicedHistBuckets);
+                if (b >= 1) {
+                    CHECK(sliced_bucket_floor_bits(b) <= bits && sliced_bucket(sliced_bucket_floor_bits(b)) == b);
+                    CHECK(sliced_bucket(sliced_bucket_floor_bits(b) - 1) == b - 1);
+                }
+                (void) prev;
+            }
+        const float one = 1.0f, tiny = 0.015f;
+        uint32_t b1, b2;
+        std::memcpy(&b1, &one, 4);
+        std::memcpy(&b2, &tiny, 4);
+        CHECK(sliced_bucket(b1) == 769 && sliced_bucket(b2) == 0 && sliced_bucket(0) == 0);
+        CHECK(sliced_bucket(0x7fc00000u) == kSlicedHistBuckets - 1); // never out of range
+    }
     if (g_fail) {
         std::fprintf(stderr, "%d check(s) failed\n", g_fail);
         return 1;

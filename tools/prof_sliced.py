@@ -1,5 +1,5 @@
 """Minimal launch loop of the bit-sliced multi-query kernel for ncu.  usage: prof_sliced.py [rows] [nq] [calls]
-Every call is: list build, sample pass, seed, full pass (scan_sliced_kernel launches 2i+1 and 2i+2)."""
+Every call is: list build, one scan_sliced_kernel launch."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
