@@ -879,6 +879,7 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     sp.meta = ws.smeta;
     sp.ghist = ws.shist;
     sp.gtau = ws.stau;
+    sp.dual = env_int("GSB_SLICED_DUAL", 1) != 0;
     // a pass: claims [0, n_mini) are each CTA's warm-up mini tile, then the tiles themselves
     auto launch = [&](uint32_t tiles, uint32_t step) -> int {
         GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));

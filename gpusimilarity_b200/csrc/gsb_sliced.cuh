@@ -75,6 +75,7 @@ struct SlicedParams {
     // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c * tile_step;
     // claim n_mini + t is tile t * tile_step (without those batches where t < n_mini)
     uint32_t n_claims, n_mini, tile_step;
+    uint32_t dual;                       // warps take two queries at a time (more independent work in flight)
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem()
@@ -254,28 +255,56 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     const uint32_t row_base32 = static_cast<uint32_t>(p.row_base);
     uint32_t phase = 0;
 
-    // One query against the rows of the tile held by lanes [lane_lo, lane_hi); NP = counter planes
-    // above "fours".
-    auto run_query = [&](auto np_tag, uint32_t j, const SlicedQuery qc, uint32_t list_base, uint32_t b0,
-                         uint32_t lane_lo, uint32_t lane_hi, float pdmin) {
-        constexpr int NP = decltype(np_tag)::value;
-        const uint32_t pq = qc.popq;
-        const uint4* lp = reinterpret_cast<const uint4*>(s_list + (qc.lofs - list_base));
+    // Common-bit counts of one query for the 32 rows of this lane's batch; NP = counter planes
+    // above "fours".  Entries are read one by one (16-bit broadcast loads: no unpacking arithmetic,
+    // the ALU pipe is the bound of this loop).
+    auto count_query = [&](auto& cnt, const SlicedQuery qc, uint32_t list_base) {
+        const uint16_t* lp = s_list + (qc.lofs - list_base);
         const uint32_t ng = qc.ngrp;
-        SlicedCount<NP> cnt;
 #pragma unroll 2
-        for (uint32_t g = 0; g < ng; g++) {
-            const uint4 e = lp[g];
-            const uint32_t x0 = *reinterpret_cast<const uint32_t*>(my_T + (e.x & 0xffffu));
-            const uint32_t x1 = *reinterpret_cast<const uint32_t*>(my_T + (e.x >> 16));
-            const uint32_t x2 = *reinterpret_cast<const uint32_t*>(my_T + (e.y & 0xffffu));
-            const uint32_t x3 = *reinterpret_cast<const uint32_t*>(my_T + (e.y >> 16));
-            const uint32_t x4 = *reinterpret_cast<const uint32_t*>(my_T + (e.z & 0xffffu));
-            const uint32_t x5 = *reinterpret_cast<const uint32_t*>(my_T + (e.z >> 16));
-            const uint32_t x6 = *reinterpret_cast<const uint32_t*>(my_T + (e.w & 0xffffu));
-            const uint32_t x7 = *reinterpret_cast<const uint32_t*>(my_T + (e.w >> 16));
-            cnt.add8(x0, x1, x2, x3, x4, x5, x6, x7);
+        for (uint32_t g = 0; g < ng; g++, lp += kSlicedGroup) {
+            uint32_t x[kSlicedGroup];
+#pragma unroll
+            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
+                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp[i]);
+            cnt.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         }
+    };
+    // Two queries at once: two independent carry-save chains keep the pipes busier.
+    auto count_queries2 = [&](auto& cnt0, auto& cnt1, const SlicedQuery qc0, const SlicedQuery qc1, uint32_t list_base) {
+        const uint16_t* lp0 = s_list + (qc0.lofs - list_base);
+        const uint16_t* lp1 = s_list + (qc1.lofs - list_base);
+        const uint32_t ng0 = qc0.ngrp, ng1 = qc1.ngrp, both = ng0 < ng1 ? ng0 : ng1;
+        for (uint32_t g = 0; g < both; g++, lp0 += kSlicedGroup, lp1 += kSlicedGroup) {
+            uint32_t x[kSlicedGroup], y[kSlicedGroup];
+#pragma unroll
+            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++) {
+                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp0[i]);
+                y[i] = *reinterpret_cast<const uint32_t*>(my_T + lp1[i]);
+            }
+            cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+            cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+        }
+        for (uint32_t g = both; g < ng0; g++, lp0 += kSlicedGroup) {
+            uint32_t x[kSlicedGroup];
+#pragma unroll
+            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
+                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp0[i]);
+            cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+        }
+        for (uint32_t g = both; g < ng1; g++, lp1 += kSlicedGroup) {
+            uint32_t y[kSlicedGroup];
+#pragma unroll
+            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
+                y[i] = *reinterpret_cast<const uint32_t*>(my_T + lp1[i]);
+            cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
+        }
+    };
+    // Filter, then the exact path for the rows of lanes [lane_lo, lane_hi) that pass it.
+    auto finish_query = [&](const auto& cnt, uint32_t j, const SlicedQuery qc, uint32_t b0, uint32_t lane_lo,
+                            uint32_t lane_hi, float pdmin) {
+        constexpr int NP = std::remove_reference_t<decltype(cnt)>::kPlanes - 3;
+        const uint32_t pq = qc.popq;
         // this lane's bound: its batch has no row with fewer than pdmin set bits
         const uint32_t ml = max(static_cast<uint32_t>(qc.m), sliced_lane_min(qc.tq, static_cast<float>(pq) + pdmin));
         uint32_t ge = cnt.at_least_lane(ml);
@@ -327,6 +356,21 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                         atomicAdd(&sp.ghist[(uint64_t) j * kSlicedHistBuckets + bucket], static_cast<unsigned int>(__popc(peers)));
                 }
             }
+        }
+    };
+
+    auto run_single = [&](uint32_t j, const SlicedQuery qc, bool live, bool small, uint32_t list_base, uint32_t b0,
+                          uint32_t lane_lo, uint32_t lane_hi, float pdmin) {
+        if (!live)
+            return;
+        if (small) {
+            SlicedCount<4> cnt;
+            count_query(cnt, qc, list_base);
+            finish_query(cnt, j, qc, b0, lane_lo, lane_hi, pdmin);
+        } else {
+            SlicedCount<8> cnt;
+            count_query(cnt, qc, list_base);
+            finish_query(cnt, j, qc, b0, lane_lo, lane_hi, pdmin);
         }
     };
 
@@ -386,8 +430,9 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             }
         }
         cta_sync<NT>();
-        // ---- phase B: warps take queries one at a time
+        // ---- phase B: warps take queries one or two at a time
         const float my_pdmin = s_pdmin[lane];
+        const uint32_t take = sp.dual ? 2u : 1u;
         for (uint32_t blk = 0; blk < n_blocks; blk++) {
             if (blk > 0) {
                 cta_sync<NT>(); // every warp has left the previous block
@@ -401,17 +446,28 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             for (;;) {
                 uint32_t j = 0;
                 if (lane == 0)
-                    j = atomicAdd(&s_next_q, 1u);
+                    j = atomicAdd(&s_next_q, take);
                 j = __shfl_sync(kFull, j, 0);
                 if (j >= q_end)
                     break;
                 const SlicedQuery qc = s_qc[j];
-                if (qc.m > qc.popq)
-                    continue; // no row can reach this query's threshold any more
-                if (qc.ngrp <= 15) // <= 120 set bits: counts fit 7 planes
-                    run_query(std::integral_constant<int, 4>{}, j, qc, list_base, b0, lane_lo, nb_tile, my_pdmin);
-                else
-                    run_query(std::integral_constant<int, 8>{}, j, qc, list_base, b0, lane_lo, nb_tile, my_pdmin);
+                const bool live = qc.m <= qc.popq; // else no row can reach this query's threshold any more
+                const bool small = qc.ngrp <= 15;  // <= 120 set bits: counts fit 7 planes
+                if (take == 2 && j + 1 < q_end) {
+                    const SlicedQuery qc1 = s_qc[j + 1];
+                    const bool live1 = qc1.m <= qc1.popq, small1 = qc1.ngrp <= 15;
+                    if (live && live1 && small && small1) {
+                        SlicedCount<4> c0, c1;
+                        count_queries2(c0, c1, qc, qc1, list_base);
+                        finish_query(c0, j, qc, b0, lane_lo, nb_tile, my_pdmin);
+                        finish_query(c1, j + 1, qc1, b0, lane_lo, nb_tile, my_pdmin);
+                    } else {
+                        run_single(j, qc, live, small, list_base, b0, lane_lo, nb_tile, my_pdmin);
+                        run_single(j + 1, qc1, live1, small1, list_base, b0, lane_lo, nb_tile, my_pdmin);
+                    }
+                } else {
+                    run_single(j, qc, live, small, list_base, b0, lane_lo, nb_tile, my_pdmin);
+                }
             }
         }
         cta_sync<NT>();

@@ -85,6 +85,7 @@ GSB_HD void csa(uint32_t& h, uint32_t& l, uint32_t a, uint32_t b, uint32_t c)
 // Running bit-sliced counters of one lane: column r of (ones, twos, fours, hi[0..NP)) is the number
 // of words added so far that had bit r set.
 template <int NP> struct SlicedCount {
+    static constexpr int kPlanes = 3 + NP;
     uint32_t ones = 0, twos = 0, fours = 0;
     uint32_t hi[NP];
     GSB_HD SlicedCount()

@@ -8,6 +8,7 @@ from gpusimilarity_b200._lib import check, lib
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000_000
 nq = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
 K = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+fast = len(sys.argv) > 4  # any 4th argument: bit-sliced kernel only
 dev = torch.device("cuda", 0)
 db = gsb.FingerprintDB.synthetic(rows, device=0, seed=0x5EED5EED, plant_period=max(64, rows // 4000))
 qrows = np.linspace(0, rows - 1, nq).astype(np.int64)
@@ -28,9 +29,14 @@ def run(group):
 
 
 results = {}
-for name, mode, sample, group in (("bit-sliced", "3", "0", 1024), ("bit-sliced + sample pass", "3", "1", 1024),
-                                  ("popc", "2", "0", 256)):
-    os.environ["GSB_BATCH_KERNEL"], os.environ["GSB_SLICED_SAMPLE"] = mode, sample
+variants = (("bit-sliced", {"GSB_BATCH_KERNEL": "3"}, 1024),
+            ("bit-sliced, one query per warp", {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_DUAL": "0"}, 1024),
+            ("bit-sliced + sample pass", {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_SAMPLE": "1"}, 1024),
+            ("popc", {"GSB_BATCH_KERNEL": "2"}, 256))
+for name, env, group in variants[:2] if fast else variants:
+    for key in ("GSB_BATCH_KERNEL", "GSB_SLICED_DUAL", "GSB_SLICED_SAMPLE"):
+        os.environ.pop(key, None)
+    os.environ.update(env)
     run(group); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); run(group); b.record(); b.synchronize()
@@ -38,6 +44,8 @@ for name, mode, sample, group in (("bit-sliced", "3", "0", 1024), ("bit-sliced +
     results[name] = keys.cpu().numpy().astype(np.uint64).copy()
     print(f"{name}: rows={rows} nq={nq} k={K}: {ms:.2f} ms -> {nq / ms * 1e3:.1f} q/s, "
           f"{rows * nq / ms / 1e6:.1f} G row*query/s")
+if fast:
+    sys.exit(0)
 print("bit-sliced == popc:", bool(np.array_equal(results["bit-sliced"], results["popc"])),
       "; with sample pass == popc:", bool(np.array_equal(results["bit-sliced + sample pass"], results["popc"])))
 rec = torch.zeros(K + 2, dtype=torch.int64, device=dev)
