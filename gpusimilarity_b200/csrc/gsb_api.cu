@@ -841,7 +841,6 @@ void fill_batch_params(const gsb_db* db, const Shard& sh, uint32_t nq, uint32_t 
 int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
                         float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
 {
-    constexpr int kWarps = 16;
     int smem_max = 0, sms = 0;
     int rc = smem_limit(sh.device, &smem_max);
     if (rc)
@@ -868,8 +867,16 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
                                                                          ws.spopq, ws.smeta);
     g_launches++;
     GSB_CUDA(cudaGetLastError());
-    GSB_CUDA(cudaFuncSetAttribute(gsb::scan_sliced_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    // warps per CTA (one CTA per SM): 32 = one batch of a tile per warp in the transposition and eight
+    // warps per scheduler to hide the shared-memory and ALU latencies of the counting loop
+    const int warps = env_int("GSB_SLICED_WARPS", 32);
+    void* kernel = warps == 16   ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<16>)
+                   : warps == 24 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<24>)
+                   : warps == 32 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<32>)
+                                 : nullptr;
+    if (!kernel)
+        return fail(GSB_ERR_INVALID, "GSB_SLICED_WARPS must be 16, 24 or 32");
+    GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     gsb::SlicedParams sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.lists = ws.slists;
@@ -887,8 +894,7 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         sp.n_claims = sp.n_mini + tiles;
         sp.tile_step = step;
         void* args[] = {&sp};
-        GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_sliced_kernel<kWarps>), dim3(grid),
-                                             dim3(kWarps * 32), args, smem, st));
+        GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(warps * 32), args, smem, st));
         g_launches++;
         return GSB_OK;
     };

@@ -82,6 +82,15 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
+// 32-bit shared-memory load at base + off.  The add is written as a multiply-add so that it can go
+// to the FMA pipe: the logic (ALU) pipe is what bounds the counting loop.
+__device__ __forceinline__ uint32_t lds_u32(uint32_t base, uint32_t off)
+{
+    uint32_t addr, v;
+    asm("mad.lo.u32 %0, %1, 1, %2;" : "=r"(addr) : "r"(off), "r"(base));
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
 // Lists, popcounts and query blocks from the raw queries ([nq][32] words): one thread per query.
 __global__ void __launch_bounds__(kMaxSlicedQueries, 1)
@@ -251,7 +260,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     if (n_blocks == 1)
         load_lists(0);
 
-    const uint8_t* my_T = tile + sliced_lane_base(lane);
+    const uint32_t my_T32 = smem_u32(tile + sliced_lane_base(lane)); // this lane's transposed batch
     const uint32_t row_base32 = static_cast<uint32_t>(p.row_base);
     uint32_t phase = 0;
 
@@ -261,12 +270,19 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     auto count_query = [&](auto& cnt, const SlicedQuery qc, uint32_t list_base) {
         const uint16_t* lp = s_list + (qc.lofs - list_base);
         const uint32_t ng = qc.ngrp;
-#pragma unroll 2
-        for (uint32_t g = 0; g < ng; g++, lp += kSlicedGroup) {
+        uint32_t g = 0;
+        for (; g + 2 <= ng; g += 2, lp += 2 * kSlicedGroup) {
+            uint32_t x[2 * kSlicedGroup];
+#pragma unroll
+            for (int i = 0; i < static_cast<int>(2 * kSlicedGroup); i++)
+                x[i] = lds_u32(my_T32, lp[i]);
+            cnt.add16(x);
+        }
+        if (g < ng) {
             uint32_t x[kSlicedGroup];
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
-                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp[i]);
+                x[i] = lds_u32(my_T32, lp[i]);
             cnt.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         }
     };
@@ -279,8 +295,8 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             uint32_t x[kSlicedGroup], y[kSlicedGroup];
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kSlicedGroup); i++) {
-                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp0[i]);
-                y[i] = *reinterpret_cast<const uint32_t*>(my_T + lp1[i]);
+                x[i] = lds_u32(my_T32, lp0[i]);
+                y[i] = lds_u32(my_T32, lp1[i]);
             }
             cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
             cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
@@ -289,14 +305,14 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             uint32_t x[kSlicedGroup];
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
-                x[i] = *reinterpret_cast<const uint32_t*>(my_T + lp0[i]);
+                x[i] = lds_u32(my_T32, lp0[i]);
             cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         }
         for (uint32_t g = both; g < ng1; g++, lp1 += kSlicedGroup) {
             uint32_t y[kSlicedGroup];
 #pragma unroll
             for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
-                y[i] = *reinterpret_cast<const uint32_t*>(my_T + lp1[i]);
+                y[i] = lds_u32(my_T32, lp1[i]);
             cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
         }
     };

@@ -66,7 +66,14 @@ static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint
         for (uint32_t l = 0; l < 32; l++) {
             SlicedCount<NP> cnt;
             const size_t base = sliced_lane_base(l);
-            for (size_t g = 0; g < list.size(); g += 8) {
+            size_t g = 0;
+            for (; g + 16 <= list.size() && (qi & 1); g += 16) { // odd queries: pairs of groups through add16
+                uint32_t x[16];
+                for (int i = 0; i < 16; i++)
+                    x[i] = rd32(tile, base + list[g + i]);
+                cnt.add16(x);
+            }
+            for (; g < list.size(); g += 8) {
                 uint32_t x[8];
                 for (int i = 0; i < 8; i++)
                     x[i] = rd32(tile, base + list[g + i]);

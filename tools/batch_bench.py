@@ -29,12 +29,15 @@ def run(group):
 
 
 results = {}
-variants = (("bit-sliced", {"GSB_BATCH_KERNEL": "3"}, 1024),
-            ("bit-sliced, one query per warp", {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_DUAL": "0"}, 1024),
-            ("bit-sliced + sample pass", {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_SAMPLE": "1"}, 1024),
-            ("popc", {"GSB_BATCH_KERNEL": "2"}, 256))
-for name, env, group in variants[:2] if fast else variants:
-    for key in ("GSB_BATCH_KERNEL", "GSB_SLICED_DUAL", "GSB_SLICED_SAMPLE"):
+variants = [("bit-sliced", {"GSB_BATCH_KERNEL": "3"}, 1024)]
+if not fast:
+    variants += [(f"bit-sliced, {w} warps, {'two queries' if d else 'one query'} per warp",
+                  {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_WARPS": str(w), "GSB_SLICED_DUAL": str(d)}, 1024)
+                 for w in (32, 24, 16) for d in (1, 0)]
+    variants += [("bit-sliced + sample pass", {"GSB_BATCH_KERNEL": "3", "GSB_SLICED_SAMPLE": "1"}, 1024),
+                 ("popc", {"GSB_BATCH_KERNEL": "2"}, 256)]
+for name, env, group in variants:
+    for key in ("GSB_BATCH_KERNEL", "GSB_SLICED_DUAL", "GSB_SLICED_SAMPLE", "GSB_SLICED_WARPS"):
         os.environ.pop(key, None)
     os.environ.update(env)
     run(group); torch.cuda.synchronize()
