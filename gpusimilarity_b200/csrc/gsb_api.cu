@@ -128,7 +128,7 @@ struct Workspace {
     unsigned long long* bout_host = nullptr;
     uint32_t bk_cap = 0, bnq_cap = 0;
     int bgrid = 0;
-    // bit-sliced multi-query kernel: query lists and the sample pass's results
+    // bit-sliced multi-query kernel: query lists, shared thresholds and score histograms
     uint16_t* slists = nullptr;            // [kMaxSlicedQueries][1024] set-bit entries
     uint32_t* slofs = nullptr;
     uint16_t* sngrp = nullptr;
@@ -136,7 +136,6 @@ struct Workspace {
     gsb::SlicedMeta* smeta = nullptr;
     unsigned long long* stau = nullptr;    // [kMaxSlicedQueries] thresholds shared by the CTAs of a pass
     unsigned int* shist = nullptr;         // [kMaxSlicedQueries][kSlicedHistBuckets] candidate score histograms
-    unsigned long long* ssample = nullptr; // [bnq_cap][bk_cap + 2] sample pass results
 };
 
 struct Shard {
@@ -362,7 +361,6 @@ void ws_free(Shard& sh)
     cudaFree(ws.bsurv);
     cudaFree(ws.bqueries);
     cudaFree(ws.bout);
-    cudaFree(ws.ssample);
     cudaFree(ws.slists);
     cudaFree(ws.slofs);
     cudaFree(ws.sngrp);
@@ -675,11 +673,11 @@ BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, flo
         return kBatchPopc;
     if (mode == 3)
         return kBatchSliced;
-    // The bit-sliced kernel pays a transposition per tile (worth it from ~16 queries on) and scores
-    // every row at or above a positive cutoff exactly (survivor count): low cutoffs let most rows
-    // through and are better served by the POPC kernel.
-    const bool cutoff_ok = !(cutoff > 0.0f) || cutoff >= 0.25f;
-    return n_queries >= 16 && cutoff_ok ? kBatchSliced : kBatchPopc;
+    // The bit-sliced kernel pays a transposition per tile: worth it from ~16 queries on.  (A low
+    // positive cutoff sends many rows through its exact path, but even with every row on that
+    // path it stays ahead of the POPC kernel.)
+    (void) cutoff;
+    return n_queries >= 16 ? kBatchSliced : kBatchPopc;
 }
 
 uint32_t batch_max_queries(BatchKernel which)
@@ -733,10 +731,9 @@ int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid, uint32_t nq)
         cudaFree(ws.bout);
         cudaFree(ws.bsurv);
         cudaFree(ws.bqueries);
-        cudaFree(ws.ssample);
         if (ws.bout_host)
             cudaFreeHost(ws.bout_host);
-        ws.bcand = ws.bqlists = ws.bout = ws.bout_host = ws.bsurv = ws.ssample = nullptr;
+        ws.bcand = ws.bqlists = ws.bout = ws.bout_host = ws.bsurv = nullptr;
         ws.bqcounts = ws.bqueries = nullptr;
         const int g = std::max(grid, ws.bgrid);
         const uint32_t kc = std::max(k, ws.bk_cap);
@@ -748,7 +745,6 @@ int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid, uint32_t nq)
         GSB_CUDA(cudaMalloc(&ws.bqlists, static_cast<size_t>(g) * nqc * kc * 8));
         GSB_CUDA(cudaMalloc(&ws.bqcounts, static_cast<size_t>(g) * nqc * 4));
         GSB_CUDA(cudaMalloc(&ws.bout, nqc * (kc + 2ull) * 8));
-        GSB_CUDA(cudaMalloc(&ws.ssample, nqc * (kc + 2ull) * 8));
         GSB_CUDA(cudaMallocHost(&ws.bout_host, nqc * (kc + 2ull) * 8));
         GSB_CUDA(cudaMalloc(&ws.bsurv, nqc * 8));
         GSB_CUDA(cudaMemset(ws.bsurv, 0, nqc * 8));
@@ -836,8 +832,8 @@ void fill_batch_params(const gsb_db* db, const Shard& sh, uint32_t nq, uint32_t 
     p.out_survivors = out_surv;
 }
 
-// Bit-sliced kernel over one shard (gsb_sliced.cuh): query lists, a strided sample pass that
-// yields a threshold per query, then the full pass.  Everything is queued on `st`.
+// Bit-sliced kernel over one shard (gsb_sliced.cuh): query lists, then one pass.  Everything is
+// queued on `st`.
 int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
                         float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
 {
@@ -886,39 +882,16 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     sp.meta = ws.smeta;
     sp.ghist = ws.shist;
     sp.gtau = ws.stau;
-    sp.dual = env_int("GSB_SLICED_DUAL", 1) != 0;
-    // a pass: claims [0, n_mini) are each CTA's warm-up mini tile, then the tiles themselves
-    auto launch = [&](uint32_t tiles, uint32_t step) -> int {
-        GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));
-        sp.n_mini = std::min<uint32_t>(static_cast<uint32_t>(grid), tiles);
-        sp.n_claims = sp.n_mini + tiles;
-        sp.tile_step = step;
-        void* args[] = {&sp};
-        GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(warps * 32), args, smem, st));
-        g_launches++;
-        return GSB_OK;
-    };
-    GSB_CUDA(cudaMemsetAsync(ws.stau, 0, static_cast<size_t>(nq) * sizeof(unsigned long long), st));
-    // ---- optional sample pass (GSB_SLICED_SAMPLE=1): every step-th tile, ~1.5 % of the shard but at
-    // least 4 tiles per CTA; its k-th key per query (minus one, so that the key itself stays
-    // eligible) seeds the full pass.  Off by default: the CTAs of one pass already share their
-    // thresholds through the grid-wide score histograms.
-    const uint32_t sample_claims = std::max<uint32_t>(4u * grid, n_tiles / 64u);
-    const bool sample = env_int("GSB_SLICED_SAMPLE", 0) != 0 && static_cast<uint64_t>(sample_claims) * 4u <= n_tiles;
-    if (sample) {
-        unsigned long long* skeys = ws.ssample;
-        unsigned long long* ssurv = skeys + static_cast<size_t>(nq) * k;
-        uint32_t* scnt = reinterpret_cast<uint32_t*>(ssurv + nq);
-        fill_batch_params(db, sh, nq, k, cutoff, d_queries, skeys, scnt, ssurv, &sp.b);
-        rc = launch(sample_claims, n_tiles / sample_claims);
-        if (rc)
-            return rc;
-        gsb::sliced_seed_tau_kernel<<<(nq + 255) / 256, 256, 0, st>>>(skeys, scnt, nq, k, ws.stau);
-        g_launches++;
-        GSB_CUDA(cudaGetLastError());
-    }
     fill_batch_params(db, sh, nq, k, cutoff, d_queries, out_keys, out_n, out_surv, &sp.b);
-    return launch(n_tiles, 1);
+    // claims [0, n_mini) are each CTA's warm-up mini tile, then the tiles themselves
+    sp.n_mini = std::min<uint32_t>(static_cast<uint32_t>(grid), n_tiles);
+    sp.n_claims = sp.n_mini + n_tiles;
+    GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));
+    GSB_CUDA(cudaMemsetAsync(ws.stau, 0, static_cast<size_t>(nq) * sizeof(unsigned long long), st));
+    void* args[] = {&sp};
+    GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(warps * 32), args, smem, st));
+    g_launches++;
+    return GSB_OK;
 }
 
 // One pass over one shard for nq <= batch_max_queries(which) queries already in device memory.
@@ -1467,7 +1440,7 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
         which = kBatchPopc; // GSB_BATCH_KERNEL=0 only switches the host-buffer API to looping
     if (n_queries < 1 || n_queries > static_cast<int>(batch_max_queries(which)))
         return fail(GSB_ERR_INVALID, "1..256 queries per call (1..1024 where the bit-sliced kernel applies: "
-                                     "1024-bit rows, 16 or more queries, cutoff <= 0 or >= 0.25)");
+                                     "1024-bit rows, 16 or more queries)");
     std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), which,

@@ -27,8 +27,7 @@
 //     path.  A CTA's first tile is a 128-row mini tile so that the warm-up (threshold 0: every
 //     row is a candidate) stays cheap.
 //
-// Dense queries are just longer lists (no fallback).  GSB_SLICED_SAMPLE=1 adds a strided ~1.5 %
-// sample pass whose k-th keys seed the full pass (useful only where CTAs cannot share thresholds).
+// Dense queries are just longer lists (no fallback).
 #pragma once
 
 #include "gsb_batch.cuh"
@@ -72,10 +71,9 @@ struct SlicedParams {
     const SlicedMeta* meta;
     unsigned int* ghist;                 // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
     unsigned long long* gtau;            // [nq] thresholds shared by all CTAs; starting values on entry
-    // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c * tile_step;
-    // claim n_mini + t is tile t * tile_step (without those batches where t < n_mini)
-    uint32_t n_claims, n_mini, tile_step;
-    uint32_t dual;                       // warps take two queries at a time (more independent work in flight)
+    // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c;
+    // claim n_mini + t is tile t (without those batches where t < n_mini)
+    uint32_t n_claims, n_mini;
 };
 
 __device__ __forceinline__ void fence_proxy_async_smem()
@@ -145,15 +143,6 @@ sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uin
         meta->n_blocks = nb;
         meta->total_entries = nq ? s_scan[nq - 1] : 0u;
     }
-}
-
-// Thresholds for the full pass from a sample pass: the k-th key of the sample stays eligible.
-__global__ void sliced_seed_tau_kernel(const unsigned long long* keys, const uint32_t* counts, uint32_t nq, uint32_t k,
-                                       unsigned long long* tau)
-{
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < nq && k > 0 && counts[j] >= k && keys[(uint64_t) j * k + k - 1] > tau[j] + 1ull)
-        tau[j] = keys[(uint64_t) j * k + k - 1] - 1ull;
 }
 
 // Descending sort of list[0, n), n <= 64, by one warp (keys are distinct: they carry the row);
@@ -286,36 +275,6 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             cnt.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         }
     };
-    // Two queries at once: two independent carry-save chains keep the pipes busier.
-    auto count_queries2 = [&](auto& cnt0, auto& cnt1, const SlicedQuery qc0, const SlicedQuery qc1, uint32_t list_base) {
-        const uint16_t* lp0 = s_list + (qc0.lofs - list_base);
-        const uint16_t* lp1 = s_list + (qc1.lofs - list_base);
-        const uint32_t ng0 = qc0.ngrp, ng1 = qc1.ngrp, both = ng0 < ng1 ? ng0 : ng1;
-        for (uint32_t g = 0; g < both; g++, lp0 += kSlicedGroup, lp1 += kSlicedGroup) {
-            uint32_t x[kSlicedGroup], y[kSlicedGroup];
-#pragma unroll
-            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++) {
-                x[i] = lds_u32(my_T32, lp0[i]);
-                y[i] = lds_u32(my_T32, lp1[i]);
-            }
-            cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-            cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
-        }
-        for (uint32_t g = both; g < ng0; g++, lp0 += kSlicedGroup) {
-            uint32_t x[kSlicedGroup];
-#pragma unroll
-            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
-                x[i] = lds_u32(my_T32, lp0[i]);
-            cnt0.add8(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
-        }
-        for (uint32_t g = both; g < ng1; g++, lp1 += kSlicedGroup) {
-            uint32_t y[kSlicedGroup];
-#pragma unroll
-            for (int i = 0; i < static_cast<int>(kSlicedGroup); i++)
-                y[i] = lds_u32(my_T32, lp1[i]);
-            cnt1.add8(y[0], y[1], y[2], y[3], y[4], y[5], y[6], y[7]);
-        }
-    };
     // Filter, then the exact path for the rows of lanes [lane_lo, lane_hi) that pass it.
     auto finish_query = [&](const auto& cnt, uint32_t j, const SlicedQuery qc, uint32_t b0, uint32_t lane_lo,
                             uint32_t lane_hi, float pdmin) {
@@ -375,21 +334,6 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         }
     };
 
-    auto run_single = [&](uint32_t j, const SlicedQuery qc, bool live, bool small, uint32_t list_base, uint32_t b0,
-                          uint32_t lane_lo, uint32_t lane_hi, float pdmin) {
-        if (!live)
-            return;
-        if (small) {
-            SlicedCount<4> cnt;
-            count_query(cnt, qc, list_base);
-            finish_query(cnt, j, qc, b0, lane_lo, lane_hi, pdmin);
-        } else {
-            SlicedCount<8> cnt;
-            count_query(cnt, qc, list_base);
-            finish_query(cnt, j, qc, b0, lane_lo, lane_hi, pdmin);
-        }
-    };
-
     for (uint32_t it = 0;; it++) {
         // everybody is done with the tile buffer (queries / select round of the previous tile)
         fence_proxy_async_smem();
@@ -399,7 +343,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             break;
         const bool mini = claim < sp.n_mini;
         const uint32_t t_idx = mini ? claim : claim - sp.n_mini;
-        const uint32_t b0 = t_idx * sp.tile_step * kSlicedTileBatches;
+        const uint32_t b0 = t_idx * kSlicedTileBatches;
         uint32_t nb_tile = p.n_batches - b0 < kSlicedTileBatches ? p.n_batches - b0 : kSlicedTileBatches;
         uint32_t lane_lo = 0;
         if (mini)
@@ -446,9 +390,8 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             }
         }
         cta_sync<NT>();
-        // ---- phase B: warps take queries one or two at a time
+        // ---- phase B: warps take queries a few at a time
         const float my_pdmin = s_pdmin[lane];
-        const uint32_t take = sp.dual ? 2u : 1u;
         for (uint32_t blk = 0; blk < n_blocks; blk++) {
             if (blk > 0) {
                 cta_sync<NT>(); // every warp has left the previous block
@@ -460,29 +403,30 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             const uint32_t q_end = n_blocks == 1 ? nq : sp.meta->blk_start[blk + 1];
             const uint32_t list_base = n_blocks == 1 ? 0u : s_qc[sp.meta->blk_start[blk]].lofs;
             for (;;) {
-                uint32_t j = 0;
-                if (lane == 0)
+                uint32_t j = 0, take = 1;
+                if (lane == 0) { // four at a time while plenty are left, then one by one (balanced finish)
+                    const uint32_t seen = *reinterpret_cast<volatile unsigned int*>(&s_next_q);
+                    take = seen + 8u * CW < q_end ? 4u : 1u;
                     j = atomicAdd(&s_next_q, take);
+                }
                 j = __shfl_sync(kFull, j, 0);
+                take = __shfl_sync(kFull, take, 0);
                 if (j >= q_end)
                     break;
-                const SlicedQuery qc = s_qc[j];
-                const bool live = qc.m <= qc.popq; // else no row can reach this query's threshold any more
-                const bool small = qc.ngrp <= 15;  // <= 120 set bits: counts fit 7 planes
-                if (take == 2 && j + 1 < q_end) {
-                    const SlicedQuery qc1 = s_qc[j + 1];
-                    const bool live1 = qc1.m <= qc1.popq, small1 = qc1.ngrp <= 15;
-                    if (live && live1 && small && small1) {
-                        SlicedCount<4> c0, c1;
-                        count_queries2(c0, c1, qc, qc1, list_base);
-                        finish_query(c0, j, qc, b0, lane_lo, nb_tile, my_pdmin);
-                        finish_query(c1, j + 1, qc1, b0, lane_lo, nb_tile, my_pdmin);
+                const uint32_t j_end = j + take < q_end ? j + take : q_end;
+                for (; j < j_end; j++) {
+                    const SlicedQuery qc = s_qc[j];
+                    if (qc.m > qc.popq)
+                        continue; // no row can reach this query's threshold any more
+                    if (qc.ngrp <= 15) { // <= 120 set bits: counts fit 7 planes
+                        SlicedCount<4> cnt;
+                        count_query(cnt, qc, list_base);
+                        finish_query(cnt, j, qc, b0, lane_lo, nb_tile, my_pdmin);
                     } else {
-                        run_single(j, qc, live, small, list_base, b0, lane_lo, nb_tile, my_pdmin);
-                        run_single(j + 1, qc1, live1, small1, list_base, b0, lane_lo, nb_tile, my_pdmin);
+                        SlicedCount<8> cnt;
+                        count_query(cnt, qc, list_base);
+                        finish_query(cnt, j, qc, b0, lane_lo, nb_tile, my_pdmin);
                     }
-                } else {
-                    run_single(j, qc, live, small, list_base, b0, lane_lo, nb_tile, my_pdmin);
                 }
             }
         }

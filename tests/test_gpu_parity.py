@@ -347,7 +347,7 @@ def test_sliced_kernel_sizes_and_ragged_tiles(monkeypatch, n_rows):
 @pytest.mark.parametrize("n_queries,k,grid", [(37, 100, 0), (300, 100, 0), (1030, 10, 0), (40, 512, 0), (64, 100, 8)])
 def test_sliced_kernel_ties_blocks_and_groups(monkeypatch, n_queries, k, grid):
     """Tie groups, empty rows, more than 1024 queries (two passes), k = 512, and with GSB_GRID=8 a
-    grid small enough that the sample pass (threshold seeding) runs at this size."""
+    small grid: many tiles per CTA, thresholds shared between few CTAs."""
     monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
     if grid:
         monkeypatch.setenv("GSB_GRID", str(grid))
@@ -379,22 +379,22 @@ def test_sliced_kernel_dense_queries_span_list_blocks(monkeypatch):
         assert_same(res[j], OC.c_search(qs[j], rows_np, 50, 0.0), f"dense query {j}")
 
 
-def test_sliced_kernel_sample_pass_full_grid(monkeypatch):
-    """3 M rows: enough tiles for the sample pass with one CTA per SM; with and without it, and
-    against the POPC multi-query kernel."""
+def test_sliced_kernel_full_grid_against_popc_kernel(monkeypatch):
+    """3 M rows, one CTA per SM, every warp count: the bit-sliced kernel against the POPC multi-query
+    kernel and the oracle."""
     rows_np = OC.c_synth_db(8, 3_000_000, 32, 1500)
     db = make_db(rows_np)
     qs = _sliced_queries(rows_np, 8, 26)
-    results = {}
-    for name, kernel, sample in (("sliced+sample", "3", "1"), ("sliced", "3", "0"), ("popc", "2", "1")):
-        monkeypatch.setenv("GSB_BATCH_KERNEL", kernel)
-        monkeypatch.setenv("GSB_SLICED_SAMPLE", sample)
-        results[name] = db.search_batch_rows(qs, 100, 0.0)
-    for j in range(len(qs)):
-        assert_same(results["sliced+sample"][j], results["popc"][j], f"sample vs popc, query {j}")
-        assert_same(results["sliced"][j], results["popc"][j], f"no sample vs popc, query {j}")
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
+    want = db.search_batch_rows(qs, 100, 0.0)
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    for warps in ("32", "24", "16"):
+        monkeypatch.setenv("GSB_SLICED_WARPS", warps)
+        got = db.search_batch_rows(qs, 100, 0.0)
+        for j in range(len(qs)):
+            assert_same(got[j], want[j], f"{warps} warps vs popc, query {j}")
     for j in (0, 1, 2, 3, 9):
-        assert_same(results["sliced+sample"][j], OC.c_search(qs[j], rows_np, 100, 0.0), f"oracle, query {j}")
+        assert_same(want[j], OC.c_search(qs[j], rows_np, 100, 0.0), f"oracle, query {j}")
 
 
 def test_multi_query_matches_single_query_path(monkeypatch):
