@@ -366,6 +366,19 @@ def test_sliced_kernel_ties_blocks_and_groups(monkeypatch, n_queries, k, grid):
             assert_same(res[j], OC.c_search(qs[j], rows_np, k, cutoff), f"sliced query {j} cutoff {cutoff}")
 
 
+def test_sliced_kernel_padded_width(monkeypatch):
+    """992-bit fingerprints live in 1024-bit device rows (zero padded): the bit-sliced kernel applies."""
+    rows_np = OC.c_synth_db(17, 120_000, 31, 43)
+    db = make_db(rows_np)
+    rng = np.random.default_rng(17)
+    qs = np.stack([O.synth_template(17, 31), np.zeros(31, np.int32), np.full(31, -1, np.int32)] +
+                  [rows_np[i] for i in rng.integers(0, 120_000, 21)])
+    for cutoff in (0.0, 0.2):
+        res = db.search_batch_rows(qs, 64, cutoff)
+        for j, got in enumerate(res):
+            assert_same(got, OC.c_search(qs[j], rows_np, 64, cutoff), f"992-bit query {j} cutoff {cutoff}")
+
+
 def test_sliced_kernel_dense_queries_span_list_blocks(monkeypatch):
     """96 half-dense queries: ~49 k list entries, three shared-memory list blocks per tile."""
     monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
