@@ -40,6 +40,7 @@ constexpr uint32_t kMaxSlicedQueries = 1024;
 constexpr uint32_t kSlicedListEntries = 20480; // u16 list entries of one query block in shared memory
 constexpr uint32_t kSlicedTileBytes = kSlicedTileBatches * kSlicedRegionBytes;
 constexpr uint32_t kSlicedMiniBatches = 4;     // batches of a CTA's very first (warm-up) tile
+constexpr uint32_t kSlicedWarmupTiles = 4;     // tiles of a CTA after which threshold sharing is overlapped
 constexpr uint32_t kSlicedPruneMin = 64;       // lists longer than this are pruned when their threshold rises
 constexpr uint32_t kSlicedWarpSortMax = 64;    // final lists up to this length are sorted by one warp
 
@@ -79,6 +80,11 @@ struct SlicedParams {
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Ask L2 for bytes that a later TMA copy will pull into shared memory.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* gmem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem), "r"(bytes) : "memory");
 }
 // 32-bit shared-memory load at base + off.  The add is written as a multiply-add so that it can go
 // to the FMA pipe: the logic (ALU) pipe is what bounds the counting loop.
@@ -168,6 +174,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
 {
     constexpr int NT = CW * 32;
     constexpr uint32_t kFull = 0xffffffffu;
+    constexpr uint32_t kTauPerThread = (kMaxSlicedQueries + NT - 1) / NT;
     const BatchParams& p = sp.b;
 
     extern __shared__ __align__(128) uint8_t smem[];
@@ -390,6 +397,72 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             }
         }
         cta_sync<NT>();
+        // ---- the next tile starts its way from HBM into L2 while this one is being counted
+        {
+            const uint32_t nclaim = s_claim[(it + 1) & 1];
+            if (lane == 0 && nclaim < sp.n_claims) {
+                const bool nmini = nclaim < sp.n_mini;
+                const uint32_t nb0 = (nmini ? nclaim : nclaim - sp.n_mini) * kSlicedTileBatches;
+                uint32_t nnb = p.n_batches - nb0 < kSlicedTileBatches ? p.n_batches - nb0 : kSlicedTileBatches;
+                if (nmini)
+                    nnb = nnb < kSlicedMiniBatches ? nnb : kSlicedMiniBatches;
+                for (uint32_t b = warp; b < nnb; b += CW)
+                    prefetch_l2_bulk(p.tiles + (uint64_t)(nb0 + b) * p.batch_stride, p.batch_bytes);
+            }
+        }
+        // ---- share thresholds across the grid.  This CTA turns the global score histograms of "its"
+        // queries (j = CTA, CTA + grid, ...) into thresholds: the floor of the bucket where the count
+        // of candidates from the top reaches k is a lower bound of the query's k-th best score over
+        // everything the grid has scanned so far.  Every thread then reads the published threshold
+        // of "its" query.  During warm-up (the first tiles of a CTA) this happens after the tile, so
+        // that the very next tile already profits; later at the start of a tile, where the loads
+        // overlap with the counting and the values are adopted one tile late.
+        unsigned long long tau_seen[kTauPerThread];
+        auto share_thresholds = [&]() {
+            for (uint32_t j = blockIdx.x + warp * gridDim.x; j < nq; j += CW * gridDim.x) {
+                const uint4* row = reinterpret_cast<const uint4*>(sp.ghist + (uint64_t) j * kSlicedHistBuckets) + lane * 8;
+                uint32_t c[32]; // this lane's 32 consecutive buckets
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint4 v = __ldcg(row + i);
+                    c[4 * i] = v.x, c[4 * i + 1] = v.y, c[4 * i + 2] = v.z, c[4 * i + 3] = v.w;
+                }
+                uint32_t mine = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    mine += c[i];
+                uint32_t incl = mine; // candidates in this lane's buckets and above
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_down_sync(kFull, incl, d);
+                    if (lane + d < 32)
+                        incl += v;
+                }
+                const unsigned reach = __ballot_sync(kFull, incl >= p.k);
+                if (reach == 0)
+                    continue; // fewer than k candidates so far
+                if (lane == 31u - __clz(reach)) {
+                    uint32_t acc = incl - mine, bstar = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int i = 31; i >= 0; i--) {
+                        acc += c[i];
+                        if (!found && acc >= p.k) {
+                            found = true;
+                            bstar = lane * 32 + i;
+                        }
+                    }
+                    if (bstar >= 1) // candidates must beat tau strictly; the bucket floor itself stays eligible
+                        atomicMax(&sp.gtau[j], (static_cast<unsigned long long>(sliced_bucket_floor_bits(bstar)) << 32) - 1ull);
+                }
+            }
+#pragma unroll
+            for (uint32_t i = 0; i < kTauPerThread; i++)
+                tau_seen[i] = tid + i * NT < nq ? __ldcg(&sp.gtau[tid + i * NT]) : 0ull;
+        };
+        const bool warming_up = it < kSlicedWarmupTiles;
+        if (!warming_up)
+            share_thresholds();
         // ---- phase B: warps take queries a few at a time
         const float my_pdmin = s_pdmin[lane];
         for (uint32_t blk = 0; blk < n_blocks; blk++) {
@@ -431,51 +504,14 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             }
         }
         cta_sync<NT>();
-        // ---- between tiles: share thresholds across the grid.  This CTA turns the global score
-        // histograms of "its" queries (j = CTA, CTA + grid, ...) into thresholds: the floor of the
-        // bucket where the count of candidates from the top reaches k is a lower bound of the
-        // query's k-th best score over everything the grid has scanned so far.
-        for (uint32_t j = blockIdx.x + warp * gridDim.x; j < nq; j += CW * gridDim.x) {
-            const uint4* row = reinterpret_cast<const uint4*>(sp.ghist + (uint64_t) j * kSlicedHistBuckets) + lane * 8;
-            uint32_t c[32]; // this lane's 32 consecutive buckets
+        // ---- between tiles: adopt the shared thresholds
+        if (warming_up)
+            share_thresholds();
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint4 v = __ldcg(row + i);
-                c[4 * i] = v.x, c[4 * i + 1] = v.y, c[4 * i + 2] = v.z, c[4 * i + 3] = v.w;
-            }
-            uint32_t mine = 0;
-#pragma unroll
-            for (int i = 0; i < 32; i++)
-                mine += c[i];
-            uint32_t incl = mine; // candidates in this lane's buckets and above
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t v = __shfl_down_sync(kFull, incl, d);
-                if (lane + d < 32)
-                    incl += v;
-            }
-            const unsigned reach = __ballot_sync(kFull, incl >= p.k);
-            if (reach == 0)
-                continue; // fewer than k candidates so far
-            if (lane == 31u - __clz(reach)) {
-                uint32_t acc = incl - mine, bstar = 0;
-                bool found = false;
-#pragma unroll
-                for (int i = 31; i >= 0; i--) {
-                    acc += c[i];
-                    if (!found && acc >= p.k) {
-                        found = true;
-                        bstar = lane * 32 + i;
-                    }
-                }
-                if (bstar >= 1) // candidates must beat tau strictly; the bucket floor itself stays eligible
-                    atomicMax(&sp.gtau[j], (static_cast<unsigned long long>(sliced_bucket_floor_bits(bstar)) << 32) - 1ull);
-            }
-        }
-        for (uint32_t j = tid; j < nq; j += NT) {
-            const unsigned long long t = __ldcg(&sp.gtau[j]);
-            if (t > s_tau[j]) {
-                s_tau[j] = t;
+        for (uint32_t i = 0; i < kTauPerThread; i++) {
+            const uint32_t j = tid + i * NT;
+            if (j < nq && tau_seen[i] > s_tau[j]) {
+                s_tau[j] = tau_seen[i];
                 update_filter(j);
                 s_qc[j].flags |= kSlicedDirty;
             }
