@@ -217,10 +217,14 @@ GSB_HD float sliced_tq(float ts)
 GSB_HD uint32_t sliced_lane_min(float tq, float pq_plus_pdmin)
 {
     const float x = tq * pq_plus_pdmin - 0.001f; // the product is off by < 2^-13 for sums up to 2048
+#ifdef __CUDA_ARCH__
+    return __float2uint_ru(x); // ceil; saturating: negative values and NaN give 0
+#else
     if (!(x > 0.0f))
         return 0u;
     const uint32_t f = static_cast<uint32_t>(x);
     return static_cast<float>(f) < x ? f + 1u : f; // ceil
+#endif
 }
 
 // Global per-query score histogram (threshold sharing between CTAs): monotone bucket of a score's
