@@ -1453,6 +1453,8 @@ int gsb_db_batch_max_queries(const gsb_db* db, uint32_t k, int n_queries, float 
 {
     if (!db || !out_max)
         return fail(GSB_ERR_INVALID, "null argument");
+    if (!db->uploaded)
+        return fail(GSB_ERR_STATE, "the device layout is chosen at upload: call gsb_db_upload first");
     BatchKernel which = batch_kernel_choice(db, k, std::max(n_queries, 2), cutoff);
     *out_max = batch_max_queries(which == kBatchNone ? kBatchPopc : which);
     return GSB_OK;

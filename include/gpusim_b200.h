@@ -134,7 +134,8 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
                                uint32_t k, float cutoff, gsb_key* d_out_keys, uint32_t* d_out_n,
                                uint64_t* d_out_survivors);
 /* Queries one gsb_db_search_batch_device call accepts for this k / batch size / cutoff: 1024
- * where the bit-sliced kernel applies (see gsb_db_search_batch), else 256. */
+ * where the bit-sliced kernel applies (see gsb_db_search_batch), else 256.  The database must
+ * have been uploaded (GSB_ERR_STATE otherwise: the device layout is chosen there). */
 int gsb_db_batch_max_queries(const gsb_db* db, uint32_t k, int n_queries, float cutoff, uint32_t* out_max);
 /* Merge of all-gathered per-rank batch records (per rank: [n_queries][k] keys, [n_queries]
  * survivors, [n_queries] counts, u64 each): one CTA per query. */

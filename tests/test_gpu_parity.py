@@ -366,6 +366,28 @@ def test_sliced_kernel_ties_blocks_and_groups(monkeypatch, n_queries, k, grid):
             assert_same(res[j], OC.c_search(qs[j], rows_np, k, cutoff), f"sliced query {j} cutoff {cutoff}")
 
 
+def test_batch_kernel_choice(monkeypatch):
+    """Host-side dispatch of multi-query searches: queries per pass over the database."""
+    import ctypes as C
+    from gpusimilarity_b200._lib import check, lib
+
+    def max_queries(db, k, nq, cutoff):
+        out = C.c_uint32(0)
+        check(lib().gsb_db_batch_max_queries(db._h, k, nq, cutoff, C.byref(out)))
+        return out.value
+    monkeypatch.delenv("GSB_BATCH_KERNEL", raising=False)
+    wide = make_db(O.synth_db(1, 100, 32, 0))
+    narrow = make_db(O.synth_db(1, 100, 8, 0))
+    assert max_queries(wide, 100, 1024, 0.0) == 1024      # bit-sliced kernel
+    assert max_queries(wide, 100, 1024, 0.1) == 1024      # ... for every cutoff
+    assert max_queries(wide, 100, 8, 0.0) == 256          # few queries: POPC kernel
+    assert max_queries(narrow, 100, 1024, 0.0) == 256     # narrow rows: POPC kernel
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
+    assert max_queries(wide, 100, 1024, 0.0) == 256
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    assert max_queries(wide, 100, 2, 0.0) == 1024
+
+
 def test_sliced_kernel_padded_width(monkeypatch):
     """992-bit fingerprints live in 1024-bit device rows (zero padded): the bit-sliced kernel applies."""
     rows_np = OC.c_synth_db(17, 120_000, 31, 43)

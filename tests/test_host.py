@@ -68,7 +68,16 @@ def test_gpu_entry_points_fail_loudly_without_device(small_fsim, small_db):
     with pytest.raises(gsb.GsbError):
         db.search_rows(small_db[0], 10, 0.0)
     with pytest.raises(gsb.GsbError):
+        db.search_batch_rows(np.stack([small_db[0]] * 20), 10, 0.0)   # multi-query path: no fallback either
+    with pytest.raises(gsb.GsbError):
         gsb.FingerprintDB.synthetic(1000)
+
+
+def test_batch_max_queries_needs_an_uploaded_database():
+    db = gsb.FingerprintDB(1024, 10, "k", [O.synth_db(1, 10, 32, 0)])
+    out = C.c_uint32(0)
+    rc = _lib.lib().gsb_db_batch_max_queries(db._h, 100, 1024, 0.0, C.byref(out))
+    assert rc == _lib.GSB_ERR_STATE and b"upload" in _lib.lib().gsb_last_error()
 
 
 def test_constructor_validation():
