@@ -673,11 +673,11 @@ BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, flo
         return kBatchPopc;
     if (mode == 3)
         return kBatchSliced;
-    // The bit-sliced kernel pays a transposition per tile: worth it from ~16 queries on.  (A low
-    // positive cutoff sends many rows through its exact path, but even with every row on that
-    // path it stays ahead of the POPC kernel.)
+    // The bit-sliced kernel pays a transposition per tile: measured cross-over between 4 and 8
+    // queries (profiles/r01_sweep.md).  (A low positive cutoff sends many rows through its exact
+    // path, but even with every row on that path it stays ahead of the POPC kernel.)
     (void) cutoff;
-    return n_queries >= 16 ? kBatchSliced : kBatchPopc;
+    return n_queries >= 6 ? kBatchSliced : kBatchPopc;
 }
 
 uint32_t batch_max_queries(BatchKernel which)
@@ -1440,7 +1440,7 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
         which = kBatchPopc; // GSB_BATCH_KERNEL=0 only switches the host-buffer API to looping
     if (n_queries < 1 || n_queries > static_cast<int>(batch_max_queries(which)))
         return fail(GSB_ERR_INVALID, "1..256 queries per call (1..1024 where the bit-sliced kernel applies: "
-                                     "1024-bit rows, 16 or more queries)");
+                                     "1024-bit rows, 6 or more queries)");
     std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), which,

@@ -380,7 +380,8 @@ def test_batch_kernel_choice(monkeypatch):
     narrow = make_db(O.synth_db(1, 100, 8, 0))
     assert max_queries(wide, 100, 1024, 0.0) == 1024      # bit-sliced kernel
     assert max_queries(wide, 100, 1024, 0.1) == 1024      # ... for every cutoff
-    assert max_queries(wide, 100, 8, 0.0) == 256          # few queries: POPC kernel
+    assert max_queries(wide, 100, 8, 0.0) == 1024
+    assert max_queries(wide, 100, 4, 0.0) == 256          # few queries: POPC kernel
     assert max_queries(narrow, 100, 1024, 0.0) == 256     # narrow rows: POPC kernel
     monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
     assert max_queries(wide, 100, 1024, 0.0) == 256

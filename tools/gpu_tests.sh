@@ -1,7 +1,8 @@
 #!/bin/bash
+# smoke() + the whole `-m gpu` suite on one B200.
 set -u
 mkdir -p gpurun_out
 timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
 rc=$?; echo "smoke rc=$rc"; tail -3 gpurun_out/smoke.log
-timeout -s KILL 1200 python -m pytest tests -q -m gpu --timeout 300 > gpurun_out/pytest_gpu.log 2>&1
+timeout -s KILL 1500 python -m pytest tests -q -m gpu --timeout 600 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?"; tail -25 gpurun_out/pytest_gpu.log
