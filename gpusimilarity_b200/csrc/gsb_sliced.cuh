@@ -72,8 +72,8 @@ struct SlicedParams {
     const SlicedMeta* meta;
     unsigned int* ghist;                 // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
     unsigned long long* gtau;            // [nq] thresholds shared by all CTAs; starting values on entry
-    // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c;
-    // claim n_mini + t is tile t (without those batches where t < n_mini)
+    // claims [0, n_mini) are mini tiles: batches [0, kSlicedMiniBatches) of tile c, the warm-up of
+    // CTA c; claim n_mini + t is tile t (without those batches where t < n_mini)
     uint32_t n_claims, n_mini;
 };
 
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     __shared__ __align__(8) uint64_t s_full[CW];
     __shared__ unsigned long long s_stage_tau;
     __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_next_q, s_need_select;
-    __shared__ unsigned int s_claim[2];
+    __shared__ unsigned int s_claim[3]; // tile claims of this, the next and the next-but-one iteration
     __shared__ float s_pdmin[kSlicedTileBatches]; // smallest row popcount of each batch of the tile
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     if (tid == 0) {
         s_alive = 0;
         s_need_select = 0;
-        s_claim[0] = atomicAdd(&p.ctrl->next_batch, 1u);
+        // claims below n_mini are the mini tiles, one per CTA and handed out statically (every CTA
+        // warms up on its own); the tiles proper are claimed dynamically, two iterations ahead
+        s_claim[0] = blockIdx.x < sp.n_mini ? blockIdx.x : sp.n_mini + atomicAdd(&p.ctrl->next_batch, 1u);
+        s_claim[1] = sp.n_mini + atomicAdd(&p.ctrl->next_batch, 1u);
     }
     if (lane == 0) {
         mbar_init(&s_full[warp], 1);
@@ -345,7 +348,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         // everybody is done with the tile buffer (queries / select round of the previous tile)
         fence_proxy_async_smem();
         cta_sync<NT>();
-        const uint32_t claim = s_claim[it & 1];
+        const uint32_t claim = s_claim[it % 3];
         if (claim >= sp.n_claims)
             break;
         const bool mini = claim < sp.n_mini;
@@ -366,8 +369,21 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                              p.batch_bytes, &s_full[warp]);
         }
         if (tid == 0) {
-            s_claim[(it + 1) & 1] = atomicAdd(&p.ctrl->next_batch, 1u); // next tile: hides the atomic's latency
+            s_claim[(it + 2) % 3] = sp.n_mini + atomicAdd(&p.ctrl->next_batch, 1u); // claimed two tiles ahead
             s_next_q = 0;
+        }
+        // the next tile starts its way from HBM into L2 now: it has this whole tile's time to arrive
+        {
+            const uint32_t nclaim = s_claim[(it + 1) % 3];
+            if (lane == 0 && nclaim < sp.n_claims) {
+                const bool nmini = nclaim < sp.n_mini;
+                const uint32_t nb0 = (nmini ? nclaim : nclaim - sp.n_mini) * kSlicedTileBatches;
+                uint32_t nnb = p.n_batches - nb0 < kSlicedTileBatches ? p.n_batches - nb0 : kSlicedTileBatches;
+                if (nmini)
+                    nnb = nnb < kSlicedMiniBatches ? nnb : kSlicedMiniBatches;
+                for (uint32_t b = warp; b < nnb; b += CW)
+                    prefetch_l2_bulk(p.tiles + (uint64_t)(nb0 + b) * p.batch_stride, p.batch_bytes);
+            }
         }
         if (n_blocks > 1)
             load_lists(0);
@@ -397,19 +413,6 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             }
         }
         cta_sync<NT>();
-        // ---- the next tile starts its way from HBM into L2 while this one is being counted
-        {
-            const uint32_t nclaim = s_claim[(it + 1) & 1];
-            if (lane == 0 && nclaim < sp.n_claims) {
-                const bool nmini = nclaim < sp.n_mini;
-                const uint32_t nb0 = (nmini ? nclaim : nclaim - sp.n_mini) * kSlicedTileBatches;
-                uint32_t nnb = p.n_batches - nb0 < kSlicedTileBatches ? p.n_batches - nb0 : kSlicedTileBatches;
-                if (nmini)
-                    nnb = nnb < kSlicedMiniBatches ? nnb : kSlicedMiniBatches;
-                for (uint32_t b = warp; b < nnb; b += CW)
-                    prefetch_l2_bulk(p.tiles + (uint64_t)(nb0 + b) * p.batch_stride, p.batch_bytes);
-            }
-        }
         // ---- share thresholds across the grid.  This CTA turns the global score histograms of "its"
         // queries (j = CTA, CTA + grid, ...) into thresholds: the floor of the bucket where the count
         // of candidates from the top reaches k is a lower bound of the query's k-th best score over

@@ -283,6 +283,14 @@ def test_partition_invariance_at_full_size(n):
     assert np.array_equal(f32bits(O.tanimoto_scores_gpu(q, fps, 0.0)),
                           f32bits(np.concatenate([scores[:20], scores[-20:]])))
     c_rows, c_scores, c_approx = whole.search_rows(q, k, 0.08)       # survivors add up over the parts
+    # BASELINE configs[4] at this size: one pass of the bit-sliced multi-query kernel must give, query
+    # by query, what the single-query kernel gives (rows, score bits, survivor counts)
+    rng = np.random.default_rng(n)
+    qs = np.stack([q] + [whole.getFingerprint(int(r)) for r in rng.integers(0, n, 23)])
+    for cutoff in (0.0, 0.08):
+        batched = whole.search_batch_rows(qs, 100, cutoff)
+        for j in range(0, len(qs), 3 if cutoff else 1):
+            assert_same(batched[j], whole.search_rows(qs[j], 100, cutoff), f"full-size batch, query {j}, cutoff {cutoff}")
     whole.close()
     per = n // parts
     cand_rows, cand_scores, part_approx = [], [], 0
