@@ -51,6 +51,19 @@ GSB_HD uint32_t sliced_lane_base(uint32_t l)
     return l * kSlicedRegionBytes + 4u * l;
 }
 
+// Byte permute (PRMT): result byte i = byte (sel >> 4i) & 7 of the pair {y, x} (x = bytes 0-3).
+GSB_HD uint32_t byte_perm(uint32_t x, uint32_t y, uint32_t sel)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, y, sel);
+#else
+    const uint64_t pair = (static_cast<uint64_t>(y) << 32) | x;
+    uint32_t r = 0;
+    for (int i = 0; i < 4; i++)
+        r |= static_cast<uint32_t>((pair >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+#endif
+}
 template <int J, uint32_t M> GSB_HD void transpose32_stage(uint32_t (&a)[32])
 {
 GSB_UNROLL
@@ -58,9 +71,19 @@ GSB_UNROLL
 GSB_UNROLL
         for (int i = 0; i < J; i++) {
             const int k = k0 + i;
-            const uint32_t t = ((a[k] >> J) ^ a[k + J]) & M;
-            a[k + J] ^= t;
-            a[k] ^= t << J;
+            if (J == 16) { // whole 16-bit halves and bytes move with one byte permute per word
+                const uint32_t lo = byte_perm(a[k], a[k + J], 0x5410), hi = byte_perm(a[k], a[k + J], 0x7632);
+                a[k] = lo;
+                a[k + J] = hi;
+            } else if (J == 8) {
+                const uint32_t lo = byte_perm(a[k], a[k + J], 0x6240), hi = byte_perm(a[k], a[k + J], 0x7351);
+                a[k] = lo;
+                a[k + J] = hi;
+            } else {
+                const uint32_t t = ((a[k] >> J) ^ a[k + J]) & M;
+                a[k + J] ^= t;
+                a[k] ^= t << J;
+            }
         }
     }
 }
