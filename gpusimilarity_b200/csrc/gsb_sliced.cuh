@@ -2,8 +2,9 @@
 //
 // scan_batch_kernel (gsb_batch.cuh) pays 32 AND + 32 POPC per row and query and is bound by the
 // POPC pipe (16 lanes/clk/SM).  This kernel gets the same common-bit counts — hence bit-identical
-// scores (reference TanimotoFunctor, fingerprintdb_cuda.cu:89-103) — from ~5 LOP3-class
-// instructions per SET BIT of the query and 32 rows:
+// scores (reference TanimotoFunctor, fingerprintdb_cuda.cu:89-103) — from ~5.5 instructions per SET
+// BIT of the query and 1024 rows (one list entry, one address add, one shared-memory word and
+// 2.25 LOP3 per lane and 32 rows):
 //
 //   * a tile is 32 consecutive 32-row batches (1024 rows).  The CTA pulls the tile into shared
 //     memory with TMA bulk copies and transposes every batch in place (32x32 bit-matrix transposes
@@ -17,17 +18,18 @@
 //     score <= common / (popc(q) + pd_min - common) with pd_min the smallest row popcount of the
 //     lane's batch — one bit-sliced compare; only the rare rows that pass are scored exactly
 //     (tanimoto_div, popcount trailer) and appended to the query's candidate list, with the same
-//     key, cutoff and survivor rules as the other kernels.  Select rounds, per-CTA lists and the grid-wide merge are shared with
-//     scan_batch_kernel (batch_select_round / batch_finish).
-//
+//     key, cutoff and survivor rules as the other kernels.  Select rounds, per-CTA lists and the
+//     grid-wide merge are shared with scan_batch_kernel (batch_select_round / batch_finish);
 //   * thresholds are shared by the whole grid: every candidate is counted in a global score
-//     histogram of its query; between tiles each CTA turns the histograms of "its" queries into
-//     thresholds (floor of the bucket where the count from the top reaches k), publishes them,
-//     and picks up everybody else's.  After the first few tiles almost no row takes the exact
-//     path.  A CTA's first tile is a 128-row mini tile so that the warm-up (threshold 0: every
-//     row is a candidate) stays cheap.
+//     histogram of its query; each CTA turns the histograms of "its" queries into thresholds
+//     (floor of the bucket where the count from the top reaches k), publishes them, and picks up
+//     everybody else's.  After the first few tiles almost no row takes the exact path.  A CTA's
+//     first tile is a 128-row mini tile so that the warm-up (threshold 0: every row is a
+//     candidate) stays cheap.
 //
-// Dense queries are just longer lists (no fallback).
+// Dense queries are just longer lists (no fallback).  One CTA per SM, 32 warps, ~215 KB of shared
+// memory: the tile (135 KB, single buffer: the next tile is prefetched into L2 meanwhile), the row
+// popcounts, the lists of up to 1024 queries (in blocks of 40 KB) and 36 bytes of state per query.
 #pragma once
 
 #include "gsb_batch.cuh"
@@ -59,7 +61,6 @@ constexpr uint32_t kSlicedPerQueryBytes = 8 + 8 + 4 + sizeof(SlicedQuery);
 // Query blocks: consecutive queries whose lists fit the shared-memory list area together.
 struct SlicedMeta {
     uint32_t n_blocks;
-    uint32_t total_entries;
     uint32_t blk_start[kMaxSlicedQueries + 1];
 };
 
@@ -147,7 +148,6 @@ sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uin
         }
         meta->blk_start[++nb] = nq;
         meta->n_blocks = nb;
-        meta->total_entries = nq ? s_scan[nq - 1] : 0u;
     }
 }
 

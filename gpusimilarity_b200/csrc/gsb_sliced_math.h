@@ -30,7 +30,6 @@ constexpr uint32_t kSlicedTileBatches = 32;   // 32-row batches per tile: lane l
 constexpr uint32_t kSlicedRegionBytes = 4224; // shared memory per batch: 1025 transposed words + lane skew
 constexpr uint32_t kSlicedZeroPos = 1024;     // bit position whose word is always zero (list padding)
 constexpr uint32_t kSlicedGroup = 8;          // list entries consumed per carry-save round
-constexpr uint32_t kSlicedMaxPlanes = 11;     // common <= 1024
 
 // Word index of bit position `pos` (0..1024) inside a lane's transposed batch.  The rotation by
 // the word column (pos >> 5) makes the transposition's stores conflict free (lane = column writes
