@@ -669,7 +669,7 @@ BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, flo
     if (mode == 0 || !db->layout.rowpop || db->layout.dev_words > 32 || db->fold_factor != 1 || k < 1 ||
         k > gsb::kMaxBatchK || n_queries < 2)
         return kBatchNone;
-    if (db->layout.dev_words != 32 || mode == 2)
+    if (mode == 2)
         return kBatchPopc;
     if (mode == 3)
         return kBatchSliced;
@@ -843,8 +843,10 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         return rc;
     GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
     const uint32_t nqp = (nq + 7u) & ~7u;
-    const uint32_t smem = gsb::kSlicedTileBytes + gsb::kSlicedTileBatches * gsb::kBatchRows * 2 +
-                          gsb::kSlicedListEntries * 2 + nqp * gsb::kSlicedPerQueryBytes;
+    const uint32_t dev_words = db->layout.dev_words;
+    const uint32_t smem = gsb::kSlicedTileBatches * gsb::sliced_region_bytes(dev_words) +
+                          gsb::kSlicedTileBatches * gsb::kBatchRows * 2 + gsb::kSlicedListEntries * 2 +
+                          nqp * gsb::kSlicedPerQueryBytes;
     if (smem + 2048 > static_cast<uint32_t>(smem_max))
         return fail(GSB_ERR_INVALID, "the bit-sliced multi-query kernel does not fit this device's shared memory");
     const uint32_t n_tiles = (sh.n_tiles + gsb::kSlicedTileBatches - 1) / gsb::kSlicedTileBatches;
@@ -859,19 +861,26 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         return rc;
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
-    gsb::sliced_build_lists_kernel<<<1, gsb::kMaxSlicedQueries, 0, st>>>(d_queries, nq, ws.slists, ws.slofs, ws.sngrp,
-                                                                         ws.spopq, ws.smeta);
+    gsb::sliced_build_lists_kernel<<<1, gsb::kMaxSlicedQueries, 0, st>>>(d_queries, nq, dev_words, ws.slists, ws.slofs,
+                                                                         ws.sngrp, ws.spopq, ws.smeta);
     g_launches++;
     GSB_CUDA(cudaGetLastError());
     // warps per CTA (one CTA per SM): 32 = one batch of a tile per warp in the transposition and eight
     // warps per scheduler to hide the shared-memory and ALU latencies of the counting loop
     const int warps = env_int("GSB_SLICED_WARPS", 32);
-    void* kernel = warps == 16   ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<16>)
-                   : warps == 24 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<24>)
-                   : warps == 32 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<32>)
-                                 : nullptr;
+    void* kernel = nullptr;
+    if (dev_words == 32)
+        kernel = warps == 16   ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<32, 16>)
+                 : warps == 24 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<32, 24>)
+                 : warps == 32 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<32, 32>)
+                               : nullptr;
+    else if (warps == 32) // narrower rows: the default shape only
+        kernel = dev_words == 16  ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<16, 32>)
+                 : dev_words == 8 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<8, 32>)
+                 : dev_words == 4 ? reinterpret_cast<void*>(gsb::scan_sliced_kernel<4, 32>)
+                                  : nullptr;
     if (!kernel)
-        return fail(GSB_ERR_INVALID, "GSB_SLICED_WARPS must be 16, 24 or 32");
+        return fail(GSB_ERR_INVALID, "GSB_SLICED_WARPS must be 16, 24 or 32 (32 for rows narrower than 1024 bits)");
     GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     gsb::SlicedParams sp;
     std::memset(&sp, 0, sizeof(sp));
@@ -1440,7 +1449,7 @@ int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_
         which = kBatchPopc; // GSB_BATCH_KERNEL=0 only switches the host-buffer API to looping
     if (n_queries < 1 || n_queries > static_cast<int>(batch_max_queries(which)))
         return fail(GSB_ERR_INVALID, "1..256 queries per call (1..1024 where the bit-sliced kernel applies: "
-                                     "1024-bit rows, 6 or more queries)");
+                                     "6 or more queries)");
     std::lock_guard<std::mutex> lock(db->mu);
     Shard& sh = const_cast<Shard&>(db->shards[0]);
     return batch_launch_shard(db, sh, static_cast<cudaStream_t>(stream), which,

@@ -1,4 +1,5 @@
-// Bit-sliced multi-query scan for 1024-bit rows (BASELINE config "batched 1024 queries, top-100").
+// Bit-sliced multi-query scan for rows of 128 to 1024 bits (BASELINE config "batched 1024 queries,
+// top-100"; the description below is for 1024-bit rows, narrower rows only make the tile smaller).
 //
 // scan_batch_kernel (gsb_batch.cuh) pays 32 AND + 32 POPC per row and query and is bound by the
 // POPC pipe (16 lanes/clk/SM).  This kernel gets the same common-bit counts — hence bit-identical
@@ -40,7 +41,6 @@ namespace gsb
 
 constexpr uint32_t kMaxSlicedQueries = 1024;
 constexpr uint32_t kSlicedListEntries = 20480; // u16 list entries of one query block in shared memory
-constexpr uint32_t kSlicedTileBytes = kSlicedTileBatches * kSlicedRegionBytes;
 constexpr uint32_t kSlicedMiniBatches = 4;     // batches of a CTA's very first (warm-up) tile
 constexpr uint32_t kSlicedWarmupTiles = 4;     // tiles of a CTA after which threshold sharing is overlapped
 constexpr uint32_t kSlicedPruneMin = 64;       // lists longer than this are pruned when their threshold rises
@@ -97,17 +97,17 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t base, uint32_t off)
     return v;
 }
 
-// Lists, popcounts and query blocks from the raw queries ([nq][32] words): one thread per query.
+// Lists, popcounts and query blocks from the raw queries ([nq][words]): one thread per query.
 __global__ void __launch_bounds__(kMaxSlicedQueries, 1)
-sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uint16_t* lists, uint32_t* lofs,
-                          uint16_t* ngrp, uint16_t* popq, SlicedMeta* meta)
+sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uint32_t words, uint16_t* lists,
+                          uint32_t* lofs, uint16_t* ngrp, uint16_t* popq, SlicedMeta* meta)
 {
     __shared__ uint32_t s_scan[kMaxSlicedQueries];
     const uint32_t j = threadIdx.x;
     uint32_t pc = 0;
     if (j < nq)
-        for (uint32_t w = 0; w < 32; w++)
-            pc += __popc(queries[j * 32 + w]);
+        for (uint32_t w = 0; w < words; w++)
+            pc += __popc(queries[j * words + w]);
     const uint32_t padded = (pc + kSlicedGroup - 1) / kSlicedGroup * kSlicedGroup;
     s_scan[j] = j < nq ? padded : 0u;
     __syncthreads();
@@ -124,8 +124,8 @@ sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uin
         popq[j] = static_cast<uint16_t>(pc);
         uint16_t* dst = lists + off;
         uint32_t n = 0;
-        for (uint32_t w = 0; w < 32; w++) {
-            uint32_t x = queries[j * 32 + w];
+        for (uint32_t w = 0; w < words; w++) {
+            uint32_t x = queries[j * words + w];
             while (x) {
                 const uint32_t b = __ffs(x) - 1;
                 x &= x - 1;
@@ -133,7 +133,7 @@ sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uin
             }
         }
         for (; n < padded; n++)
-            dst[n] = sliced_entry(kSlicedZeroPos);
+            dst[n] = sliced_zero_entry(words);
     }
     if (j == 0) {
         uint32_t nb = 0, used = 0;
@@ -169,10 +169,14 @@ __device__ __forceinline__ void sliced_warp_sort(unsigned long long* list, uint3
         list[r1] = k1;
 }
 
-template <int CW>
+// W = 32-bit words per row (4, 8, 16 or 32), CW = warps per CTA.
+template <int W, int CW>
 __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_constant__ SlicedParams sp)
 {
     constexpr int NT = CW * 32;
+    constexpr uint32_t kRegion = sliced_region_bytes(W);  // shared memory per batch
+    constexpr uint32_t kTileBytes = kSlicedTileBatches * kRegion;
+    constexpr uint32_t kGang = 32 / W;                    // batches one warp transposes at a time
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kTauPerThread = (kMaxSlicedQueries + NT - 1) / NT;
     const BatchParams& p = sp.b;
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     const uint32_t nq = p.nq, nqp = (nq + 7u) & ~7u;
     // shared memory carve-up
     uint8_t* tile = smem;                                                        // 32 batch regions
-    uint16_t* s_pd = reinterpret_cast<uint16_t*>(smem + kSlicedTileBytes);       // [1024] row popcounts of the tile
+    uint16_t* s_pd = reinterpret_cast<uint16_t*>(smem + kTileBytes);       // [1024] row popcounts of the tile
     uint16_t* s_list = s_pd + kSlicedTileBatches * kBatchRows;                   // [kSlicedListEntries]
     uint8_t* cursor = reinterpret_cast<uint8_t*>(s_list + kSlicedListEntries);
     SlicedQuery* s_qc = reinterpret_cast<SlicedQuery*>(cursor);                  // [nq]
@@ -259,7 +263,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     if (n_blocks == 1)
         load_lists(0);
 
-    const uint32_t my_T32 = smem_u32(tile + sliced_lane_base(lane)); // this lane's transposed batch
+    const uint32_t my_T32 = smem_u32(tile + sliced_lane_base(lane, W)); // this lane's transposed batch
     const uint32_t row_base32 = static_cast<uint32_t>(p.row_base);
     uint32_t phase = 0;
 
@@ -360,13 +364,17 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             nb_tile = nb_tile < kSlicedMiniBatches ? nb_tile : kSlicedMiniBatches;
         else if (t_idx < sp.n_mini)
             lane_lo = kSlicedMiniBatches; // those batches were this tile's mini tile
-        // ---- phase A: TMA the tile in (every warp its own batches), transpose in place
-        const uint32_t n_mine = warp < nb_tile ? (nb_tile - warp + CW - 1) / CW : 0u;
+        // ---- phase A: TMA the tile in (every warp its own batches), transpose in place.  A warp
+        // handles gangs of 32 / W batches: lane = (batch of the gang, word column).
+        uint32_t n_mine = 0;
+        for (uint32_t g0 = warp * kGang; g0 < nb_tile; g0 += CW * kGang)
+            n_mine += nb_tile - g0 < kGang ? nb_tile - g0 : kGang;
         if (lane == 0 && n_mine) {
             mbar_arrive_expect_tx(&s_full[warp], n_mine * p.batch_bytes);
-            for (uint32_t b = warp; b < nb_tile; b += CW)
-                tma_bulk_g2s(tile + (size_t) b * kSlicedRegionBytes, p.tiles + (uint64_t)(b0 + b) * p.batch_stride,
-                             p.batch_bytes, &s_full[warp]);
+            for (uint32_t g0 = warp * kGang; g0 < nb_tile; g0 += CW * kGang)
+                for (uint32_t b = g0; b < g0 + kGang && b < nb_tile; b++)
+                    tma_bulk_g2s(tile + (size_t) b * kRegion, p.tiles + (uint64_t)(b0 + b) * p.batch_stride,
+                                 p.batch_bytes, &s_full[warp]);
         }
         if (tid == 0) {
             s_claim[(it + 2) % 3] = sp.n_mini + atomicAdd(&p.ctrl->next_batch, 1u); // claimed two tiles ahead
@@ -390,26 +398,42 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
         if (n_mine) {
             mbar_wait(&s_full[warp], phase);
             phase ^= 1u;
-            for (uint32_t b = warp; b < nb_tile; b += CW) {
-                uint8_t* region = tile + (size_t) b * kSlicedRegionBytes;
+            const uint32_t sub = lane / W, col = lane % W;
+            for (uint32_t g0 = warp * kGang; g0 < nb_tile; g0 += CW * kGang) {
+                const uint32_t b = g0 + sub; // this lane's batch of the gang
+                const bool have = b < nb_tile;
+                uint8_t* region = tile + (size_t) b * kRegion;
                 const uint32_t* raw = reinterpret_cast<const uint32_t*>(region);
-                uint32_t x[32]; // lane = word column, x[r] = that word of row r
+                uint32_t x[32]; // x[r] = word `col` of row r
 #pragma unroll
                 for (int r = 0; r < 32; r++)
-                    x[r] = raw[r * 32 + lane];
-                const uint16_t pd = reinterpret_cast<const uint16_t*>(region + (size_t) kBatchRows * 128)[lane];
-                const uint32_t pd_lo = __reduce_min_sync(kFull, static_cast<uint32_t>(pd));
-                if (lane == 0)
-                    s_pdmin[b] = static_cast<float>(pd_lo);
-                __syncwarp(); // in place: every lane has read the batch before anyone overwrites it
-                transpose32(x);
-                uint32_t* T = reinterpret_cast<uint32_t*>(tile + sliced_lane_base(b));
+                    x[r] = have ? raw[r * W + col] : 0u;
+                // row popcounts of every batch of the gang: lane r holds row r's
+                uint16_t pd[kGang];
 #pragma unroll
-                for (int bb = 0; bb < 32; bb++)
-                    T[lane * 32 + ((bb + lane) & 31)] = x[bb]; // == sliced_word_index(lane * 32 + bb)
-                if (lane == 0)
-                    T[kSlicedZeroPos] = 0u;
-                s_pd[b * kBatchRows + lane] = pd;
+                for (uint32_t s = 0; s < kGang; s++) {
+                    const uint32_t bs = g0 + s;
+                    pd[s] = bs < nb_tile
+                                ? reinterpret_cast<const uint16_t*>(tile + (size_t) bs * kRegion + (size_t) kBatchRows * W * 4)[lane]
+                                : static_cast<uint16_t>(0);
+                    const uint32_t pd_lo = __reduce_min_sync(kFull, static_cast<uint32_t>(pd[s]));
+                    if (lane == 0 && bs < nb_tile)
+                        s_pdmin[bs] = static_cast<float>(pd_lo);
+                }
+                __syncwarp(); // in place: every lane has read its batch before anyone overwrites it
+                transpose32(x);
+                if (have) {
+                    uint32_t* T = reinterpret_cast<uint32_t*>(tile + sliced_lane_base(b, W));
+#pragma unroll
+                    for (int bb = 0; bb < 32; bb++)
+                        T[col * 32 + ((bb + col) & 31)] = x[bb]; // == sliced_word_index(col * 32 + bb)
+                    if (col == 0)
+                        T[sliced_zero_index(W)] = 0u;
+                }
+#pragma unroll
+                for (uint32_t s = 0; s < kGang; s++)
+                    if (g0 + s < nb_tile)
+                        s_pd[(g0 + s) * kBatchRows + lane] = pd[s];
             }
         }
         cta_sync<NT>();

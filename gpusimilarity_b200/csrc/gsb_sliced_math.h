@@ -27,11 +27,30 @@ namespace gsb
 {
 
 constexpr uint32_t kSlicedTileBatches = 32;   // 32-row batches per tile: lane l of a warp works on batch l
-constexpr uint32_t kSlicedRegionBytes = 4224; // shared memory per batch: 1025 transposed words + lane skew
-constexpr uint32_t kSlicedZeroPos = 1024;     // bit position whose word is always zero (list padding)
+// Shared memory per batch for rows of `words` 32-bit words: words*32 + 1 transposed words (the last
+// one is always zero: list padding) + up to 124 bytes of lane skew, in whole 128-byte lines (so that
+// every region starts in bank 0); never smaller than the raw batch the TMA copy delivers.
+GSB_HD constexpr uint32_t sliced_region_bytes(uint32_t words)
+{
+    return ((words * 32u + 1u) * 4u + 124u + 127u) / 128u * 128u;
+}
+// Word index (inside a lane's transposed batch) of the word that is always zero, and the list
+// entry that points at it (padding of the lists to whole groups).
+GSB_HD constexpr uint32_t sliced_zero_index(uint32_t words)
+{
+    return words * 32u;
+}
+GSB_HD constexpr uint16_t sliced_zero_entry(uint32_t words)
+{
+    return static_cast<uint16_t>(words * 32u * 4u);
+}
+constexpr uint32_t kSlicedRegionBytes = sliced_region_bytes(32); // 1024-bit rows: 4224
+static_assert(kSlicedRegionBytes == 4224 && sliced_region_bytes(16) == 2176 && sliced_region_bytes(8) == 1152 &&
+                  sliced_region_bytes(4) == 640,
+              "regions hold the raw batch (32 rows + 64 bytes of popcounts) and the skewed transposed batch");
 constexpr uint32_t kSlicedGroup = 8;          // list entries consumed per carry-save round
 
-// Word index of bit position `pos` (0..1024) inside a lane's transposed batch.  The rotation by
+// Word index of bit position `pos` (0 .. row bits - 1) inside a lane's transposed batch.  The rotation by
 // the word column (pos >> 5) makes the transposition's stores conflict free (lane = column writes
 // 32 words that land in 32 banks); lane l's batch starts 4*l bytes into its region, so the loads
 // of one position by the 32 lanes of a warp hit 32 different banks as well.
@@ -45,9 +64,9 @@ GSB_HD uint16_t sliced_entry(uint32_t pos)
     return static_cast<uint16_t>(sliced_word_index(pos) * 4u);
 }
 // Byte offset of lane l's transposed batch inside the tile buffer.
-GSB_HD uint32_t sliced_lane_base(uint32_t l)
+GSB_HD uint32_t sliced_lane_base(uint32_t l, uint32_t words = 32)
 {
-    return l * kSlicedRegionBytes + 4u * l;
+    return l * sliced_region_bytes(words) + 4u * l;
 }
 
 // Byte permute (PRMT): result byte i = byte (sel >> 4i) & 7 of the pair {y, x} (x = bytes 0-3).

@@ -93,8 +93,8 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
  * over the same database; query q's results land at out_rows + q*k etc.  Identical results to
  * n_queries calls of gsb_db_search.  With the default layout, rows of at most 1024 bits, no fold
  * and k <= 512 the queries share ONE pass over the database per group: 1024 queries per pass
- * with the bit-sliced kernel (1024-bit rows, 6 or more queries; gsb_sliced.cuh), 256 with the
- * POPC kernel; otherwise they are searched one after the other.
+ * with the bit-sliced kernel (6 or more queries; gsb_sliced.cuh), 256 with the POPC kernel;
+ * otherwise they are searched one after the other.
  * GSB_BATCH_KERNEL=0/2/3 forces looping / the POPC kernel / the bit-sliced kernel. */
 int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words,
                         int n_queries, uint32_t k, float cutoff, uint32_t* out_rows,

@@ -34,38 +34,38 @@ static void wr32(std::vector<uint8_t>& b, size_t off, uint32_t v)
 
 template <int NP>
 static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint32_t>& rows, std::mt19937& rng,
-                        int n_queries, double density)
+                        int n_queries, double density, int W = 32)
 {
     std::bernoulli_distribution bit(density);
     for (int qi = 0; qi < n_queries; qi++) {
         uint32_t q[32];
-        for (int w = 0; w < 32; w++) {
+        for (int w = 0; w < W; w++) {
             q[w] = 0;
             for (int b = 0; b < 32; b++)
                 q[w] |= static_cast<uint32_t>(bit(rng)) << b;
         }
         // list of entries, padded to a multiple of kSlicedGroup with the zero position
         std::vector<uint16_t> list;
-        for (int w = 0; w < 32; w++)
+        for (int w = 0; w < W; w++)
             for (int b = 0; b < 32; b++)
                 if ((q[w] >> b) & 1u)
                     list.push_back(sliced_entry(w * 32 + b));
         const uint32_t pq = static_cast<uint32_t>(list.size());
         while (list.size() % kSlicedGroup)
-            list.push_back(sliced_entry(kSlicedZeroPos));
+            list.push_back(sliced_zero_entry(W));
         if (pq >= (1u << (3 + NP)))
             continue; // the caller picks NP from the list length
         // every entry is read by the 32 lanes at once: 32 different banks
         for (uint16_t e : list) {
             std::set<uint32_t> banks;
             for (uint32_t l = 0; l < 32; l++)
-                banks.insert(((sliced_lane_base(l) + e) / 4) % 32);
+                banks.insert(((sliced_lane_base(l, W) + e) / 4) % 32);
             CHECK(banks.size() == 32);
         }
         const uint32_t m = static_cast<uint32_t>(rng() % (pq + 2));
         for (uint32_t l = 0; l < 32; l++) {
             SlicedCount<NP> cnt;
-            const size_t base = sliced_lane_base(l);
+            const size_t base = sliced_lane_base(l, W);
             size_t g = 0;
             for (; g + 16 <= list.size() && (qi & 1); g += 16) { // odd queries: pairs of groups through add16
                 uint32_t x[16];
@@ -82,8 +82,8 @@ static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint
             uint32_t want_ge = 0;
             for (uint32_t r = 0; r < 32; r++) {
                 uint32_t common = 0;
-                for (int w = 0; w < 32; w++)
-                    common += __builtin_popcount(q[w] & rows[(l * 32 + r) * 32 + w]);
+                for (int w = 0; w < W; w++)
+                    common += __builtin_popcount(q[w] & rows[(l * 32 + r) * W + w]);
                 CHECK(cnt.column(r) == common);
                 if (common >= m)
                     want_ge |= 1u << r;
@@ -94,6 +94,75 @@ static void run_queries(const std::vector<uint8_t>& tile, const std::vector<uint
             }
         }
     }
+}
+
+// One tile of rows of W words: raw batches as the TMA copies leave them, in-place transposition
+// as the kernel does it (lane = word column; gangs of 32 / W batches per warp), then queries.
+static void check_width(int W, std::mt19937& rng)
+{
+    const uint32_t region_bytes = sliced_region_bytes(W), zero_pos = sliced_zero_index(W);
+    std::vector<uint8_t> tile(kSlicedTileBatches * region_bytes, 0xAB);
+    std::vector<uint32_t> rows(32 * 32 * W);
+    std::bernoulli_distribution bit(1.0 / 12);
+    for (auto& w : rows) {
+        w = 0;
+        for (int b = 0; b < 32; b++)
+            w |= static_cast<uint32_t>(bit(rng)) << b;
+    }
+    CHECK(region_bytes % 128 == 0 && region_bytes >= 32u * W * 4 + 64);
+    for (uint32_t l = 0; l < 32; l++)
+        for (uint32_t r = 0; r < 32; r++) {
+            uint32_t pc = 0;
+            for (int w = 0; w < W; w++) {
+                wr32(tile, l * region_bytes + (r * W + w) * 4, rows[(l * 32 + r) * W + w]);
+                pc += __builtin_popcount(rows[(l * 32 + r) * W + w]);
+            }
+            const uint16_t p16 = static_cast<uint16_t>(pc);
+            std::memcpy(&tile[l * region_bytes + 32 * W * 4 + r * 2], &p16, 2);
+        }
+    for (uint32_t b = 0; b < 32; b++) {
+        const size_t region = b * region_bytes;
+        std::vector<std::vector<uint32_t>> x(W, std::vector<uint32_t>(32)); // [column][register]
+        for (int col = 0; col < W; col++)
+            for (uint32_t r = 0; r < 32; r++)
+                x[col][r] = rd32(tile, region + (r * W + col) * 4);
+        // (all reads happen before any write: __syncwarp in the kernel)
+        for (int col = 0; col < W; col++) {
+            uint32_t regs[32];
+            for (int i = 0; i < 32; i++)
+                regs[i] = x[col][i];
+            transpose32(regs);
+            for (int i = 0; i < 32; i++)
+                x[col][i] = regs[i];
+        }
+        const size_t tbase = sliced_lane_base(b, W);
+        CHECK(tbase >= region && tbase + (zero_pos + 1) * 4 <= region + region_bytes);
+        for (uint32_t bb = 0; bb < 32; bb++) {
+            std::set<uint32_t> banks;
+            for (int col = 0; col < W; col++) {
+                const uint32_t idx = sliced_word_index(col * 32 + bb);
+                CHECK(idx == col * 32 + ((bb + col) & 31));
+                banks.insert(((tbase / 4) + idx) % 32);
+                wr32(tile, tbase + idx * 4, x[col][bb]);
+            }
+            CHECK(banks.size() == static_cast<size_t>(W)); // conflict-free stores within a batch
+        }
+        wr32(tile, tbase + zero_pos * 4, 0u);
+    }
+    CHECK(sliced_zero_entry(W) == zero_pos * 4);
+    // the word index is a bijection on the row's bit positions (the zero word sits right after them)
+    {
+        std::set<uint32_t> seen;
+        for (uint32_t pos = 0; pos < zero_pos; pos++)
+            seen.insert(sliced_word_index(pos));
+        CHECK(seen.size() == zero_pos && *seen.rbegin() == zero_pos - 1);
+    }
+    // sparse queries on the small counter, dense ones on the large counter
+    run_queries<4>(tile, rows, rng, 40, 1.0 / 30, W);
+    run_queries<4>(tile, rows, rng, 10, W >= 16 ? 1.0 / 10 : 1.0 / 4, W);
+    run_queries<8>(tile, rows, rng, 10, 0.5, W);
+    run_queries<8>(tile, rows, rng, 3, 1.0, W);
+    run_queries<8>(tile, rows, rng, 3, 0.0, W);
 }
 
 int main()
@@ -109,63 +178,9 @@ int main()
             for (int c = 0; c < 32; c++)
                 CHECK(((b[c] >> r) & 1u) == ((a[r] >> c) & 1u));
     }
-    // ---- tile: 32 raw batches as the TMA copies leave them (32 rows x 128 B, then 32 u16 popcounts)
-    std::vector<uint8_t> tile(kSlicedTileBatches * kSlicedRegionBytes, 0xAB);
-    std::vector<uint32_t> rows(32 * 32 * 32);
-    std::bernoulli_distribution bit(1.0 / 12);
-    for (auto& w : rows) {
-        w = 0;
-        for (int b = 0; b < 32; b++)
-            w |= static_cast<uint32_t>(bit(rng)) << b;
-    }
-    for (uint32_t l = 0; l < 32; l++)
-        for (uint32_t r = 0; r < 32; r++) {
-            uint32_t pc = 0;
-            for (uint32_t w = 0; w < 32; w++) {
-                wr32(tile, l * kSlicedRegionBytes + (r * 32 + w) * 4, rows[(l * 32 + r) * 32 + w]);
-                pc += __builtin_popcount(rows[(l * 32 + r) * 32 + w]);
-            }
-            const uint16_t p16 = static_cast<uint16_t>(pc);
-            std::memcpy(&tile[l * kSlicedRegionBytes + 4096 + r * 2], &p16, 2);
-        }
-    // ---- phase A as the kernel does it: lane = word column, registers = rows, in place
-    for (uint32_t b = 0; b < 32; b++) {
-        const size_t region = b * kSlicedRegionBytes;
-        uint32_t x[32][32]; // [lane][register]
-        for (uint32_t lane = 0; lane < 32; lane++)
-            for (uint32_t r = 0; r < 32; r++)
-                x[lane][r] = rd32(tile, region + (r * 32 + lane) * 4);
-        // (all reads happen before any write: __syncwarp in the kernel)
-        for (uint32_t lane = 0; lane < 32; lane++)
-            transpose32(x[lane]);
-        const size_t tbase = sliced_lane_base(b);
-        CHECK(tbase >= region && tbase + 1025 * 4 <= region + kSlicedRegionBytes);
-        for (uint32_t bb = 0; bb < 32; bb++) {
-            std::set<uint32_t> banks;
-            for (uint32_t lane = 0; lane < 32; lane++) {
-                const uint32_t idx = sliced_word_index(lane * 32 + bb);
-                CHECK(idx == lane * 32 + ((bb + lane) & 31));
-                banks.insert(((tbase / 4) + idx) % 32);
-                wr32(tile, tbase + idx * 4, x[lane][bb]);
-            }
-            CHECK(banks.size() == 32); // conflict-free stores
-        }
-        wr32(tile, tbase + sliced_word_index(kSlicedZeroPos) * 4, 0u);
-    }
-    CHECK(sliced_word_index(kSlicedZeroPos) == 1024);
-    // the word index is a bijection on [0, 1024]
-    {
-        std::set<uint32_t> seen;
-        for (uint32_t pos = 0; pos <= 1024; pos++)
-            seen.insert(sliced_word_index(pos));
-        CHECK(seen.size() == 1025 && *seen.rbegin() == 1024);
-    }
-    // ---- phase B: sparse queries on the small counter, dense ones on the large counter
-    run_queries<4>(tile, rows, rng, 40, 1.0 / 30);
-    run_queries<4>(tile, rows, rng, 10, 1.0 / 10);
-    run_queries<8>(tile, rows, rng, 10, 0.5);
-    run_queries<8>(tile, rows, rng, 3, 1.0);
-    run_queries<8>(tile, rows, rng, 3, 0.0);
+    // ---- tile layout, transposition and counting for every supported row width
+    for (int W : {32, 16, 8, 4})
+        check_width(W, rng);
     // ---- filter bound: smallest count whose best-case score reaches ts
     {
         auto div = [](uint32_t c, uint32_t u) { return u ? static_cast<float>(c) / static_cast<float>(u) : 0.0f / 0.0f; };

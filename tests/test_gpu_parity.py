@@ -390,11 +390,35 @@ def test_batch_kernel_choice(monkeypatch):
     assert max_queries(wide, 100, 1024, 0.1) == 1024      # ... for every cutoff
     assert max_queries(wide, 100, 8, 0.0) == 1024
     assert max_queries(wide, 100, 4, 0.0) == 256          # few queries: POPC kernel
-    assert max_queries(narrow, 100, 1024, 0.0) == 256     # narrow rows: POPC kernel
+    assert max_queries(narrow, 100, 1024, 0.0) == 1024    # narrow rows too
     monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
     assert max_queries(wide, 100, 1024, 0.0) == 256
     monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
     assert max_queries(wide, 100, 2, 0.0) == 1024
+
+
+@pytest.mark.parametrize("bits", [128, 256, 480, 512])
+def test_sliced_kernel_narrow_rows(monkeypatch, bits):
+    """Rows narrower than 1024 bits (16, 8 or 4 device words; 480 bits are padded to 512): smaller
+    tiles, gangs of batches per warp in the transposition.  Both multi-query kernels and the oracle."""
+    words = bits // 32
+    rows_np = OC.c_synth_db(bits, 150_000, words, 59)
+    rows_np[500:560] = rows_np[3]                                   # a tie group
+    rows_np[900:910] = 0
+    db = make_db(rows_np)
+    rng = np.random.default_rng(bits)
+    qs = np.stack([O.synth_template(bits, words), np.zeros(words, np.int32), np.full(words, -1, np.int32),
+                   rng.integers(-2**31, 2**31, words).astype(np.int32), rows_np[3]] +
+                  [rows_np[i] for i in rng.integers(0, 150_000, 19)])
+    for cutoff in (0.0, 0.3):
+        monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+        sliced = db.search_batch_rows(qs, 50, cutoff)
+        monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
+        popc = db.search_batch_rows(qs, 50, cutoff)
+        for j in range(len(qs)):
+            want = OC.c_search(qs[j], rows_np, 50, cutoff)
+            assert_same(sliced[j], want, f"{bits}-bit rows, bit-sliced, query {j}, cutoff {cutoff}")
+            assert_same(popc[j], want, f"{bits}-bit rows, POPC kernel, query {j}, cutoff {cutoff}")
 
 
 def test_sliced_kernel_padded_width(monkeypatch):
