@@ -844,7 +844,7 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
     const uint32_t nqp = (nq + 7u) & ~7u;
     const uint32_t dev_words = db->layout.dev_words;
-    const uint32_t smem = gsb::kSlicedTileBatches * gsb::sliced_region_bytes(dev_words) +
+    const uint32_t smem = gsb::sliced_tile_bytes(dev_words) +
                           gsb::kSlicedTileBatches * gsb::kBatchRows * 2 + gsb::kSlicedListEntries * 2 +
                           nqp * gsb::kSlicedPerQueryBytes;
     if (smem + 2048 > static_cast<uint32_t>(smem_max))

@@ -41,6 +41,14 @@ namespace gsb
 
 constexpr uint32_t kMaxSlicedQueries = 1024;
 constexpr uint32_t kSlicedListEntries = 20480; // u16 list entries of one query block in shared memory
+// The tile buffer: 32 batch regions, and never less than the staging area of the select rounds
+// (candidate keys + bucket histogram), which runs between tiles and borrows it.
+__host__ __device__ constexpr uint32_t sliced_tile_bytes(uint32_t words)
+{
+    return kSlicedTileBatches * sliced_region_bytes(words) > kBatchListCap * 8u + kBuckets * 4u
+               ? kSlicedTileBatches * sliced_region_bytes(words)
+               : kBatchListCap * 8u + kBuckets * 4u;
+}
 constexpr uint32_t kSlicedMiniBatches = 4;     // batches of a CTA's very first (warm-up) tile
 constexpr uint32_t kSlicedWarmupTiles = 4;     // tiles of a CTA after which threshold sharing is overlapped
 constexpr uint32_t kSlicedPruneMin = 64;       // lists longer than this are pruned when their threshold rises
@@ -175,7 +183,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
 {
     constexpr int NT = CW * 32;
     constexpr uint32_t kRegion = sliced_region_bytes(W);  // shared memory per batch
-    constexpr uint32_t kTileBytes = kSlicedTileBatches * kRegion;
+    constexpr uint32_t kTileBytes = sliced_tile_bytes(W);
     constexpr uint32_t kGang = 32 / W;                    // batches one warp transposes at a time
     constexpr uint32_t kFull = 0xffffffffu;
     constexpr uint32_t kTauPerThread = (kMaxSlicedQueries + NT - 1) / NT;

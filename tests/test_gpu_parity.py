@@ -419,6 +419,15 @@ def test_sliced_kernel_narrow_rows(monkeypatch, bits):
             want = OC.c_search(qs[j], rows_np, 50, cutoff)
             assert_same(sliced[j], want, f"{bits}-bit rows, bit-sliced, query {j}, cutoff {cutoff}")
             assert_same(popc[j], want, f"{bits}-bit rows, POPC kernel, query {j}, cutoff {cutoff}")
+    # many sparse queries: coarse scores, huge tie groups, lists long enough for the CTA-wide select
+    # rounds (whose staging area borrows the tile buffer — smaller than that for 128-bit rows)
+    many = np.stack([rows_np[i] for i in rng.integers(0, 150_000, 200)])
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+    sliced = db.search_batch_rows(many, 100, 0.0)
+    monkeypatch.setenv("GSB_BATCH_KERNEL", "2")
+    popc = db.search_batch_rows(many, 100, 0.0)
+    for j in range(len(many)):
+        assert_same(sliced[j], popc[j], f"{bits}-bit rows, 200 sparse queries, query {j}")
 
 
 def test_sliced_kernel_padded_width(monkeypatch):
