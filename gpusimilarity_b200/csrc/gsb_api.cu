@@ -759,17 +759,23 @@ int batch_reserve(Shard& sh, const Layout& l, uint32_t k, int grid, uint32_t nq)
 int sliced_reserve(Shard& sh)
 {
     Workspace& ws = sh.ws;
-    if (ws.smeta)
-        return GSB_OK;
     GSB_CUDA(cudaSetDevice(sh.device));
     const size_t nq = gsb::kMaxSlicedQueries;
-    GSB_CUDA(cudaMalloc(&ws.slists, nq * 1024 * sizeof(uint16_t)));
-    GSB_CUDA(cudaMalloc(&ws.slofs, nq * sizeof(uint32_t)));
-    GSB_CUDA(cudaMalloc(&ws.sngrp, nq * sizeof(uint16_t)));
-    GSB_CUDA(cudaMalloc(&ws.spopq, nq * sizeof(uint16_t)));
-    GSB_CUDA(cudaMalloc(&ws.stau, nq * sizeof(unsigned long long)));
-    GSB_CUDA(cudaMalloc(&ws.shist, nq * gsb::kSlicedHistBuckets * sizeof(unsigned int)));
-    GSB_CUDA(cudaMalloc(&ws.smeta, sizeof(gsb::SlicedMeta)));
+    // every buffer on its own: a failed allocation leaves the others in place for the next call
+    if (!ws.slists)
+        GSB_CUDA(cudaMalloc(&ws.slists, nq * 1024 * sizeof(uint16_t)));
+    if (!ws.slofs)
+        GSB_CUDA(cudaMalloc(&ws.slofs, nq * sizeof(uint32_t)));
+    if (!ws.sngrp)
+        GSB_CUDA(cudaMalloc(&ws.sngrp, nq * sizeof(uint16_t)));
+    if (!ws.spopq)
+        GSB_CUDA(cudaMalloc(&ws.spopq, nq * sizeof(uint16_t)));
+    if (!ws.stau)
+        GSB_CUDA(cudaMalloc(&ws.stau, nq * sizeof(unsigned long long)));
+    if (!ws.shist)
+        GSB_CUDA(cudaMalloc(&ws.shist, nq * gsb::kSlicedHistBuckets * sizeof(unsigned int)));
+    if (!ws.smeta)
+        GSB_CUDA(cudaMalloc(&ws.smeta, sizeof(gsb::SlicedMeta)));
     return GSB_OK;
 }
 
