@@ -1,6 +1,9 @@
-// Multi-query scan: one pass over the database scores every 32-row batch against up to
+// Multi-query scan with POPC: one pass over the database scores every 32-row batch against up to
 // kMaxBatchQueries queries held in shared memory (BASELINE config "batched 1024 queries, top-100";
-// the reference has no batching, gpusim.cpp:407-414 serves one query per request).
+// the reference has no batching, gpusim.cpp:407-414 serves one query per request).  Used for small
+// batches (fewer than 6 queries); larger ones go to the bit-sliced kernel in gsb_sliced.cuh, which
+// shares the candidate lists, select rounds and the end of the launch with this file
+// (batch_select_round, batch_finish).
 //
 // The database is read once per launch, so the kernel is bound by the POPC pipe (16 lanes/clk/SM:
 // 32 POPC per row and query), not by HBM.  Data path and work distribution are the single-query
