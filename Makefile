@@ -1,7 +1,7 @@
 # Builds the product library (sm_100a only) in-tree, plus the test-infrastructure checkers.
 NVCC   ?= /usr/local/cuda/bin/nvcc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall -cudart static
+NVFLAGS := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC,-Wall,-ffp-contract=off -cudart static
 CSRC   := gpusimilarity_b200/csrc
 LIB    := gpusimilarity_b200/libgpusim_b200.so
 

@@ -22,6 +22,18 @@ class Exchange(C.Structure):
     _fields_ = [("peer_base", C.c_uint64 * 16), ("rank", C.c_uint32), ("world", C.c_uint32), ("seq", C.c_uint64)]
 
 
+class Sink(C.Structure):
+    """gsb_sink: device-accessible result pointers of gsb_db_search_enqueue."""
+    _fields_ = [("keys", C.c_void_p), ("rows", C.c_void_p), ("scores", C.c_void_p), ("n", C.c_void_p),
+                ("approx", C.c_void_p), ("done", C.c_void_p), ("done_value", C.c_uint64)]
+
+
+GSB_QUERY_STABLE = 1
+GSB_COUNT_ERROR = 0xFFFFFFFF
+GSB_METRIC_TANIMOTO, GSB_METRIC_DICE, GSB_METRIC_TVERSKY = 0, 1, 2
+GSB_BATCH_LOOPED, GSB_BATCH_POPC, GSB_BATCH_SLICED = 0, 1, 2
+
+
 class ScanInfo(C.Structure):
     _fields_ = [("device", C.c_int), ("grid", C.c_int), ("block", C.c_int), ("stages", C.c_int),
                 ("tile_rows", C.c_uint32), ("tile_bytes", C.c_uint32), ("smem_bytes", C.c_uint32),
@@ -42,7 +54,10 @@ SIGNATURES = {
                                 C.POINTER(_P)]),
     "gsb_db_create_synthetic": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                           C.c_uint32, C.POINTER(_P)]),
+    "gsb_db_create_synthetic_sharded": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_uint64, C.c_uint64,
+                                                  C.c_uint64, C.c_uint32, C.POINTER(_P)]),
     "gsb_db_upload": (C.c_int, [_P, C.POINTER(C.c_int), C.c_int, C.c_uint]),
+    "gsb_db_set_metric": (C.c_int, [_P, C.c_int, C.c_float, C.c_float]),
     "gsb_db_destroy": (None, [_P]),
     "gsb_db_count": (C.c_uint64, [_P]),
     "gsb_db_fp_bits": (C.c_int, [_P]),
@@ -52,7 +67,10 @@ SIGNATURES = {
     "gsb_db_get_fingerprint": (C.c_int, [_P, C.c_uint64, _P]),
     "gsb_db_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_float, _P, _P,
                                 C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "gsb_db_search_async": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_float, C.POINTER(C.c_uint64)]),
+    "gsb_db_search_wait": (C.c_int, [_P, C.c_uint64, _P, _P, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "gsb_db_search_batch": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_uint32, C.c_float, _P, _P, _P, _P]),
+    "gsb_db_batch_mode": (C.c_int, [_P, C.c_uint32, C.c_int, C.c_float, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]),
     "gsb_db_search_cpu": (C.c_int, [_P, _P, C.c_int, C.c_uint32, _P, _P, C.POINTER(C.c_uint32)]),
     "gsb_db_search_device": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, _P, _P, _P]),
     "gsb_db_search_batch_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_float, _P, _P, _P]),
@@ -60,6 +78,9 @@ SIGNATURES = {
     "gsb_merge_batch_device": (C.c_int, [C.c_int, _P, _P, C.c_int, C.c_int, C.c_uint32, _P, _P, _P, _P]),
     "gsb_exchange_bytes": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "gsb_db_search_device_fused": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_float, C.POINTER(Exchange), _P, _P, _P, _P]),
+    "gsb_db_search_enqueue": (C.c_int, [_P, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_float, C.POINTER(Exchange),
+                                        C.POINTER(Sink)]),
+    "gsb_wait_word": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "gsb_merge_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, _P, _P, _P]),
     "gsb_fsim_open": (C.c_int, [C.c_char_p, C.POINTER(_P)]),
     "gsb_fsim_close": (None, [_P]),

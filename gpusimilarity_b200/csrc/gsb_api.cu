@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -24,6 +25,13 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define GSB_CPU_RELAX() _mm_pause()
+#else
+#define GSB_CPU_RELAX() std::this_thread::yield()
+#endif
 
 namespace
 {
@@ -43,6 +51,15 @@ int fail(int code, const std::string& msg)
         if (e__ != cudaSuccess)                                                                  \
             return fail(GSB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
     } while (0)
+
+// No exception may cross the C ABI (std::bad_alloc from a huge request would otherwise end in
+// std::terminate inside the host process).
+#define GSB_TRY try {
+#define GSB_CATCH                                                                                \
+    }                                                                                            \
+    catch (const std::bad_alloc&) { return fail(GSB_ERR_NOMEM, "out of host memory"); }          \
+    catch (const std::exception& e) { return fail(GSB_ERR_INVALID, std::string("exception: ") + e.what()); } \
+    catch (...) { return fail(GSB_ERR_INVALID, "unknown exception"); }
 
 int env_int(const char* name, int dflt)
 {
@@ -104,18 +121,39 @@ size_t padded_tile_bytes(const Layout& l, uint32_t n_tiles)
     return static_cast<size_t>(units) * l.unit_bytes;
 }
 
-struct Workspace {
-    cudaStream_t stream = nullptr;
+// Select state of one launch of the single-query kernel.  A shard owns TWO sets and alternates
+// between them: with programmatic dependent launch the scan of query i+1 starts while the last
+// CTA of query i is still sorting / exchanging / merging out of the other set.
+struct SelectSet {
     gsb::ScanCtrl* ctrl = nullptr;
     unsigned int* ghist = nullptr;
     unsigned long long* gfinal = nullptr;
     unsigned long long* cta_keys = nullptr;
     uint32_t* cta_counts = nullptr;
     uint64_t cta_keys_cap = 0; // entries
-    // results of the host-buffer API: [k keys][survivors u64][n u32]
-    unsigned long long* out_dev = nullptr;
-    unsigned long long* out_host = nullptr; // pinned
-    uint32_t out_cap = 0;                   // keys
+};
+
+// Result record of one host-buffer query in MAPPED pinned host memory: the last CTA of the launch
+// stores [k keys][survivors][n][done] straight into it (no cudaMemcpy, no stream synchronize: the
+// host polls the done word).  kSlots - 1 records serve gsb_db_search_async tickets, the last one
+// the synchronous calls.
+constexpr int kAsyncDepth = 4;
+constexpr int kSlots = kAsyncDepth + 1;
+constexpr int kSyncSlot = kAsyncDepth;
+struct ResultSlot {
+    unsigned long long* host = nullptr;
+    unsigned long long* dev = nullptr; // the same memory as the device sees it
+    uint32_t cap = 0;                  // keys
+};
+
+struct Workspace {
+    cudaStream_t stream = nullptr;
+    SelectSet sets[2];
+    uint64_t scan_launches = 0;          // picks the set of the next launch
+    cudaStream_t last_stream = nullptr;  // stream of the latest launch that used this workspace
+    bool launched = false;
+    cudaEvent_t order_event = nullptr;   // orders launches that arrive on different streams
+    ResultSlot slots[kSlots];
     int max_grid = 0;
     // multi-query kernel scratch (allocated on first use)
     gsb::BatchCtrl* bctrl = nullptr;
@@ -184,7 +222,27 @@ struct gsb_db {
     std::vector<Shard> shards;
     bool uploaded = false;
     uint64_t synth_seed = 0;
-    mutable std::mutex mu; // one search in flight per database, like the reference
+    // similarity metric (gsb_db_set_metric); Tanimoto unless told otherwise
+    uint32_t metric = gsb::kMetricTanimoto;
+    float alpha = 1.0f, beta = 1.0f;
+    // folded databases: the unfolded host rows registered with CUDA (mapped) for the device re-score
+    bool host_registered = false;
+    gsb::RescoreChunk* d_chunks = nullptr; // chunk table on the re-score device (shard 0's)
+    unsigned long long* rescore_host = nullptr, *rescore_dev = nullptr; // mapped pinned: candidates in, keys out
+    size_t rescore_cap = 0;
+    // queries in flight through the host-buffer API (gsb_db_search_async / _wait)
+    struct Pending {
+        uint64_t ticket = 0; // 0 = free
+        uint64_t seq = 0;    // completion word value of the launches
+        uint32_t k = 0;
+        float cutoff = 0.0f;
+        bool deferred = false; // folded / very large k: computed inside gsb_db_search_wait
+        std::vector<int32_t> query;
+    };
+    mutable Pending pending[kAsyncDepth];
+    mutable uint64_t next_ticket = 1;
+    mutable uint64_t done_seq = 0;
+    mutable std::mutex mu; // enqueue side: launch planning and workspace growth are not re-entrant
 };
 
 namespace
@@ -198,22 +256,123 @@ int smem_limit(int device, int* out)
     return GSB_OK;
 }
 
+// ---- ordering of launches that share a device --------------------------------------------------
+// Every scan kernel here lines its CTAs up on a grid-wide arrival counter, so all of them must be
+// resident together.  On ONE stream that holds by construction (a launch owns every SM it needs
+// before the next one starts; with programmatic dependent launch the successor only takes SMs the
+// predecessor has left).  Launches on DIFFERENT streams of a device could interleave their CTAs
+// and starve each other, and launches that share a shard's workspace must not overlap at all.
+// Both are ruled out lazily: when a launch arrives on another stream than the work still in flight,
+// an event recorded on that stream's tail is waited for first.  No event is recorded on the steady
+// one-stream path (an event between two kernels would also switch off their overlap).
+struct DeviceGate {
+    std::mutex mu;
+    struct Entry {
+        cudaStream_t stream;
+        int grid;
+    };
+    std::vector<Entry> inflight;
+    cudaEvent_t event = nullptr;
+};
+DeviceGate g_gates[64];
+
+int order_after(cudaStream_t later, cudaStream_t earlier, cudaEvent_t* ev)
+{
+    const cudaError_t q = cudaStreamQuery(earlier);
+    if (q != cudaErrorNotReady) { // idle (or a stream its owner has destroyed): nothing to wait for
+        cudaGetLastError();
+        return GSB_OK;
+    }
+    cudaGetLastError();
+    if (!*ev)
+        GSB_CUDA(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    GSB_CUDA(cudaEventRecord(*ev, earlier));
+    GSB_CUDA(cudaStreamWaitEvent(later, *ev, 0));
+    return GSB_OK;
+}
+
+// Called (under the database mutex) right before a grid-barrier kernel of `grid` CTAs is launched
+// on `st` for workspace `ws` of device `dev`.
+int gate_launch(int dev, Workspace& ws, cudaStream_t st, int grid)
+{
+    if (ws.launched && ws.last_stream != st) { // same workspace, other stream: never overlap
+        int rc = order_after(st, ws.last_stream, &ws.order_event);
+        if (rc)
+            return rc;
+    }
+    ws.launched = true;
+    ws.last_stream = st;
+    if (dev < 0 || dev >= 64)
+        return GSB_OK;
+    DeviceGate& g = g_gates[dev];
+    std::lock_guard<std::mutex> lock(g.mu);
+    int others = 0;
+    for (const auto& e : g.inflight)
+        if (e.stream != st)
+            others += e.grid;
+    if (others + grid > ws.max_grid) { // cannot all be resident together: run after them
+        for (const auto& e : g.inflight)
+            if (e.stream != st) {
+                int rc = order_after(st, e.stream, &g.event);
+                if (rc)
+                    return rc;
+            }
+        g.inflight.clear();
+    }
+    for (auto& e : g.inflight)
+        if (e.stream == st) {
+            e.grid = std::max(e.grid, grid);
+            return GSB_OK;
+        }
+    g.inflight.push_back({st, grid});
+    return GSB_OK;
+}
+
+void gate_forget(int dev, cudaStream_t st)
+{
+    if (dev < 0 || dev >= 64)
+        return;
+    DeviceGate& g = g_gates[dev];
+    std::lock_guard<std::mutex> lock(g.mu);
+    for (size_t i = 0; i < g.inflight.size(); i++)
+        if (g.inflight[i].stream == st) {
+            g.inflight.erase(g.inflight.begin() + i);
+            break;
+        }
+}
+
 template <int W, bool RP, int CW> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
     static thread_local int configured[64] = {0};
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
+    auto kernel = gsb::scan_topk_kernel<W, RP, CW>;
     if (dev < 64 && configured[dev] < static_cast<int>(plan.smem)) {
-        GSB_CUDA(cudaFuncSetAttribute(gsb::scan_topk_kernel<W, RP, CW>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
+        GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, plan.smem));
         configured[dev] = plan.smem;
     }
-    // cooperative launch: every CTA must be resident, the kernel lines them up on an arrival counter
-    void* args[] = {const_cast<gsb::ScanParams*>(&p)};
-    // (measured: a cooperative launch costs the same as a plain one, 57 us per back-to-back launch
-    // at 1 M rows either way)
-    GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gsb::scan_topk_kernel<W, RP, CW>), dim3(plan.grid),
-                                         dim3(CW * 32), args, plan.smem, st));
+    if (env_int("GSB_PDL", 1)) {
+        // Programmatic dependent launch: the scan of this query may start on SMs the previous query
+        // (same stream, other control set) has already left.  Residency of the whole grid is what a
+        // cooperative launch would check: grid <= SMs and one CTA fits an SM (make_plan), and
+        // gate_launch keeps other streams' grids off the device meanwhile.
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(plan.grid);
+        cfg.blockDim = dim3(CW * 32);
+        cfg.dynamicSmemBytes = plan.smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        GSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+    } else {
+        // cooperative launch: the runtime itself guarantees that every CTA is resident
+        void* args[] = {const_cast<gsb::ScanParams*>(&p)};
+        GSB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(plan.grid), dim3(CW * 32), args,
+                                             plan.smem, st));
+    }
     g_launches++;
     return GSB_OK;
 }
@@ -297,45 +456,85 @@ int make_plan(const Layout& l, const Shard& sh, uint32_t k, Plan* out)
                                      " is too large for the fused in-kernel select");
 }
 
+int set_init(SelectSet& set)
+{
+    GSB_CUDA(cudaMalloc(&set.ctrl, sizeof(gsb::ScanCtrl)));
+    GSB_CUDA(cudaMemset(set.ctrl, 0, sizeof(gsb::ScanCtrl)));
+    GSB_CUDA(cudaMalloc(&set.ghist, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMemset(set.ghist, 0, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMalloc(&set.gfinal, 32768 * 8));
+    GSB_CUDA(cudaMalloc(&set.cta_counts, sizeof(uint32_t) * 4096));
+    return GSB_OK;
+}
+
 int ws_init(Shard& sh)
 {
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
     GSB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
-    GSB_CUDA(cudaMalloc(&ws.ctrl, sizeof(gsb::ScanCtrl)));
-    GSB_CUDA(cudaMemset(ws.ctrl, 0, sizeof(gsb::ScanCtrl)));
-    GSB_CUDA(cudaMalloc(&ws.ghist, gsb::kBuckets * 4));
-    GSB_CUDA(cudaMemset(ws.ghist, 0, gsb::kBuckets * 4));
-    GSB_CUDA(cudaMalloc(&ws.gfinal, 32768 * 8));
+    for (SelectSet& set : ws.sets) {
+        int rc = set_init(set);
+        if (rc)
+            return rc;
+    }
     int sms = 0;
     GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
     ws.max_grid = sms; // persistent: one CTA per SM (shared memory allows no more), all resident
-    GSB_CUDA(cudaMalloc(&ws.cta_counts, sizeof(uint32_t) * 4096));
     return GSB_OK;
 }
 
-int ws_reserve(Shard& sh, uint32_t k, int grid, bool host_results)
+// After a launch reported an error word (grid barrier / peer flag timeout) its control sets are
+// suspect: drain the device and zero them, so that the next search starts from a clean state.
+int ws_recover(Shard& sh)
+{
+    GSB_CUDA(cudaSetDevice(sh.device));
+    GSB_CUDA(cudaDeviceSynchronize());
+    for (SelectSet& set : sh.ws.sets) {
+        GSB_CUDA(cudaMemset(set.ctrl, 0, sizeof(gsb::ScanCtrl)));
+        GSB_CUDA(cudaMemset(set.ghist, 0, gsb::kBuckets * 4));
+    }
+    if (sh.ws.bctrl)
+        GSB_CUDA(cudaMemset(sh.ws.bctrl, 0, sizeof(gsb::BatchCtrl)));
+    if (sh.ws.bsurv)
+        GSB_CUDA(cudaMemset(sh.ws.bsurv, 0, static_cast<size_t>(sh.ws.bnq_cap) * 8));
+    GSB_CUDA(cudaDeviceSynchronize());
+    return GSB_OK;
+}
+
+// slot < 0: results go to caller-provided (device) buffers, no record needed.
+int ws_reserve(Shard& sh, uint32_t k, int grid, int slot)
 {
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
     const uint64_t need = static_cast<uint64_t>(grid) * std::max<uint32_t>(k, 1);
-    if (need > ws.cta_keys_cap) {
-        if (ws.cta_keys)
-            GSB_CUDA(cudaFree(ws.cta_keys));
-        ws.cta_keys = nullptr;
-        GSB_CUDA(cudaMalloc(&ws.cta_keys, need * 8));
-        ws.cta_keys_cap = need;
+    for (SelectSet& set : ws.sets) {
+        if (need > set.cta_keys_cap) {
+            if (set.cta_keys) {
+                GSB_CUDA(cudaStreamSynchronize(ws.stream)); // a launch may still be using the old one
+                GSB_CUDA(cudaFree(set.cta_keys));
+            }
+            set.cta_keys = nullptr;
+            set.cta_keys_cap = 0;
+            GSB_CUDA(cudaMalloc(&set.cta_keys, need * 8));
+            set.cta_keys_cap = need;
+        }
     }
-    if (host_results && k > ws.out_cap) {
-        if (ws.out_dev)
-            GSB_CUDA(cudaFree(ws.out_dev));
-        if (ws.out_host)
-            GSB_CUDA(cudaFreeHost(ws.out_host));
-        ws.out_dev = ws.out_host = nullptr;
+    if (slot >= 0 && k > ws.slots[slot].cap) {
+        ResultSlot& rs = ws.slots[slot];
+        if (rs.host) {
+            GSB_CUDA(cudaStreamSynchronize(ws.stream));
+            GSB_CUDA(cudaFreeHost(rs.host));
+        }
+        rs = ResultSlot();
         const uint32_t cap = pow2ceil(std::max<uint32_t>(k, 1024));
-        GSB_CUDA(cudaMalloc(&ws.out_dev, (static_cast<size_t>(cap) + 2) * 8));
-        GSB_CUDA(cudaMallocHost(&ws.out_host, (static_cast<size_t>(cap) + 2) * 8));
-        ws.out_cap = cap;
+        void* h = nullptr;
+        GSB_CUDA(cudaHostAlloc(&h, (static_cast<size_t>(cap) + 4) * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+        std::memset(h, 0, (static_cast<size_t>(cap) + 4) * 8);
+        void* d = nullptr;
+        GSB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+        rs.host = static_cast<unsigned long long*>(h);
+        rs.dev = static_cast<unsigned long long*>(d);
+        rs.cap = cap;
     }
     return GSB_OK;
 }
@@ -344,16 +543,23 @@ void ws_free(Shard& sh)
 {
     cudaSetDevice(sh.device);
     Workspace& ws = sh.ws;
-    if (ws.stream)
+    if (ws.stream) {
+        cudaStreamSynchronize(ws.stream);
+        gate_forget(sh.device, ws.stream);
         cudaStreamDestroy(ws.stream);
-    cudaFree(ws.ctrl);
-    cudaFree(ws.ghist);
-    cudaFree(ws.gfinal);
-    cudaFree(ws.cta_keys);
-    cudaFree(ws.cta_counts);
-    cudaFree(ws.out_dev);
-    if (ws.out_host)
-        cudaFreeHost(ws.out_host);
+    }
+    if (ws.order_event)
+        cudaEventDestroy(ws.order_event);
+    for (SelectSet& set : ws.sets) {
+        cudaFree(set.ctrl);
+        cudaFree(set.ghist);
+        cudaFree(set.gfinal);
+        cudaFree(set.cta_keys);
+        cudaFree(set.cta_counts);
+    }
+    for (ResultSlot& rs : ws.slots)
+        if (rs.host)
+            cudaFreeHost(rs.host);
     cudaFree(ws.bctrl);
     cudaFree(ws.bcand);
     cudaFree(ws.bqlists);
@@ -479,10 +685,17 @@ int upload_rows(const gsb_db* db, Shard& sh)
     return GSB_OK;
 }
 
-void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k, float cutoff,
-                 gsb::ScanParams* p)
+uint64_t spin_timeout_ns()
+{
+    // wall-clock bound of the in-kernel spins (grid barrier, peer flags); GSB_SPIN_TIMEOUT_MS for tests
+    return static_cast<uint64_t>(std::max(1, env_int("GSB_SPIN_TIMEOUT_MS", 10000))) * 1000000ull;
+}
+
+// Parameters of the next single-query launch over this shard; takes the next control set.
+void fill_params(const gsb_db* db, Shard& sh, const Plan& plan, uint32_t k, float cutoff, gsb::ScanParams* p)
 {
     const Layout& l = db->layout;
+    const SelectSet& set = sh.ws.sets[sh.ws.scan_launches++ & 1];
     std::memset(p, 0, sizeof(*p));
     p->tiles = sh.tiles;
     p->n_rows = sh.n_rows;
@@ -496,11 +709,15 @@ void fill_params(const gsb_db* db, const Shard& sh, const Plan& plan, uint32_t k
     p->k = k;
     p->cutoff = cutoff;
     p->key_ceiling = ~0ull;
-    p->cta_keys = sh.ws.cta_keys;
-    p->cta_counts = sh.ws.cta_counts;
-    p->ctrl = sh.ws.ctrl;
-    p->ghist = sh.ws.ghist;
-    p->gfinal = sh.ws.gfinal;
+    p->cta_keys = set.cta_keys;
+    p->cta_counts = set.cta_counts;
+    p->ctrl = set.ctrl;
+    p->ghist = set.ghist;
+    p->gfinal = set.gfinal;
+    p->spin_timeout_ns = spin_timeout_ns();
+    p->metric = db->metric;
+    p->alpha = db->alpha;
+    p->beta = db->beta;
 }
 
 struct Cand {
@@ -517,93 +734,169 @@ inline Cand decode(unsigned long long key)
     return c;
 }
 
-// One scan per shard with a host-resident query; leaves keys/n/survivors in ws.out_host.
-int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, float cutoff,
-                    unsigned long long key_ceiling, std::vector<unsigned long long>* keys, uint64_t* survivors)
+void print_debug_times(const std::vector<unsigned long long>& h, int grid)
 {
-    std::vector<Plan> plans(db->shards.size());
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid; c++)
+        t0 = std::min(t0, h[c * 8]);
+    const char* names[7] = {"start", "(unused)", "warp0 out of work", "cta out of work", "global histogram read",
+                            "ticket", "final sort done"};
+    for (int st = 0; st < 7; st++) {
+        unsigned long long lo = ~0ull, hi = 0;
+        double sum = 0;
+        int n = 0;
+        for (int c = 0; c < grid; c++) {
+            const unsigned long long v = h[c * 8 + st];
+            if (!v)
+                continue;
+            lo = std::min(lo, v - t0), hi = std::max(hi, v - t0), sum += double(v - t0), n++;
+        }
+        if (n)
+            std::fprintf(stderr, "[gsb dbg] %-18s n=%3d min %8.1f us avg %8.1f us max %8.1f us\n", names[st], n, lo / 1e3,
+                         sum / n / 1e3, hi / 1e3);
+    }
+    unsigned long long emax = 0;
+    for (int c = 0; c < grid; c++)
+        emax = std::max(emax, h[c * 8 + 7]);
+    std::fprintf(stderr, "[gsb dbg] selects per CTA during the scan: max %llu\n", emax);
+}
+
+// One launch per shard with a host-resident query (it travels as a kernel parameter); the last CTA
+// of every launch stores the shard's record into result slot `slot` (mapped pinned memory) and then
+// the completion value `seq`.  Nothing here waits for the device.
+int enqueue_scan(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, float cutoff,
+                 unsigned long long key_ceiling, int slot, uint64_t seq)
+{
     for (size_t i = 0; i < db->shards.size(); i++) {
         Shard& sh = const_cast<Shard&>(db->shards[i]);
         if (sh.n_rows == 0)
             continue;
-        int rc = make_plan(db->layout, sh, k, &plans[i]);
+        Plan plan;
+        int rc = make_plan(db->layout, sh, k, &plan);
         if (rc)
             return rc;
-        rc = ws_reserve(sh, k, plans[i].grid, true);
+        rc = ws_reserve(sh, k, plan.grid, slot);
         if (rc)
             return rc;
         GSB_CUDA(cudaSetDevice(sh.device));
         gsb::ScanParams p;
-        fill_params(db, sh, plans[i], k, cutoff, &p);
+        fill_params(db, sh, plan, k, cutoff, &p);
         std::memcpy(p.q_host, q_dev_words, db->layout.dev_words * 4);
         p.key_ceiling = key_ceiling;
-        p.out_keys = sh.ws.out_dev;
-        p.out_survivors = sh.ws.out_dev + k;
-        p.out_n = reinterpret_cast<uint32_t*>(sh.ws.out_dev + k + 1);
+        unsigned long long* rec = sh.ws.slots[slot].dev;
+        p.out_keys = rec;
+        p.out_survivors = rec + k;
+        p.out_n = reinterpret_cast<uint32_t*>(rec + k + 1);
+        p.out_done = rec + k + 2;
+        p.out_done_value = seq;
         unsigned long long* dbg = nullptr;
         if (env_int("GSB_DEBUG_TIMES", 0)) {
-            GSB_CUDA(cudaMalloc(&dbg, plans[i].grid * 64));
-            GSB_CUDA(cudaMemsetAsync(dbg, 0, plans[i].grid * 64, sh.ws.stream));
+            GSB_CUDA(cudaMalloc(&dbg, plan.grid * 64));
+            GSB_CUDA(cudaMemsetAsync(dbg, 0, plan.grid * 64, sh.ws.stream));
             p.dbg = dbg;
         }
-        rc = launch_scan(db->layout, p, plans[i], sh.ws.stream);
+        rc = gate_launch(sh.device, sh.ws, sh.ws.stream, plan.grid);
+        if (rc)
+            return rc;
+        rc = launch_scan(db->layout, p, plan, sh.ws.stream);
         if (rc)
             return rc;
         if (dbg) { // developer aid: phase timeline of the launch (ns since the earliest CTA start)
-            std::vector<unsigned long long> h(plans[i].grid * 8);
+            std::vector<unsigned long long> h(plan.grid * 8);
             GSB_CUDA(cudaMemcpyAsync(h.data(), dbg, h.size() * 8, cudaMemcpyDeviceToHost, sh.ws.stream));
             GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
             cudaFree(dbg);
-            unsigned long long t0 = ~0ull;
-            for (int c = 0; c < plans[i].grid; c++)
-                t0 = std::min(t0, h[c * 8]);
-            const char* names[7] = {"start", "(unused)", "warp0 out of work", "cta out of work", "global histogram read",
-                                    "ticket", "final sort done"};
-            for (int s = 0; s < 7; s++) {
-                unsigned long long lo = ~0ull, hi = 0;
-                double sum = 0;
-                int n = 0;
-                for (int c = 0; c < plans[i].grid; c++) {
-                    const unsigned long long v = h[c * 8 + s];
-                    if (!v)
-                        continue;
-                    lo = std::min(lo, v - t0), hi = std::max(hi, v - t0), sum += double(v - t0), n++;
-                }
-                if (n)
-                    std::fprintf(stderr, "[gsb dbg] %-18s n=%3d min %8.1f us avg %8.1f us max %8.1f us\n", names[s], n,
-                                 lo / 1e3, sum / n / 1e3, hi / 1e3);
-            }
-            unsigned long long emax = 0;
-            for (int c = 0; c < plans[i].grid; c++)
-                emax = std::max(emax, h[c * 8 + 7]);
-            std::fprintf(stderr, "[gsb dbg] selects per CTA during the scan: max %llu\n", emax);
+            print_debug_times(h, plan.grid);
         }
-        GSB_CUDA(cudaMemcpyAsync(sh.ws.out_host, sh.ws.out_dev, (static_cast<size_t>(k) + 2) * 8,
-                                 cudaMemcpyDeviceToHost, sh.ws.stream));
     }
+    return GSB_OK;
+}
+
+// Wait until `word` (mapped pinned memory, written by the device) holds `value`.  Spins first
+// (GSB_POLL_SPIN_US, default 20 ms: a query over a full HBM takes about that long), then sleeps in
+// short steps; the stream is probed now and then so that a failed launch ends the wait.
+int wait_word(const unsigned long long* word, unsigned long long value, cudaStream_t stream)
+{
+    const volatile unsigned long long* w = word;
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long spin_us = env_int("GSB_POLL_SPIN_US", 20000);
+    const long long limit_s = std::max(1, env_int("GSB_WAIT_TIMEOUT_S", 120));
+    for (uint64_t spins = 1; *w != value; spins++) {
+        GSB_CPU_RELAX();
+        if ((spins & 0xfff) != 0)
+            continue;
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count();
+        if (stream) {
+            const cudaError_t e = cudaStreamQuery(stream);
+            if (e == cudaSuccess) { // everything queued has run: the word is there, or never will be
+                if (*w == value)
+                    break;
+                return fail(GSB_ERR_CUDA, "the search kernel finished without publishing its result");
+            }
+            if (e != cudaErrorNotReady)
+                return fail(GSB_ERR_CUDA, std::string("search kernel failed: ") + cudaGetErrorString(e));
+        }
+        if (us > limit_s * 1000000ll)
+            return fail(GSB_ERR_CUDA, "timed out waiting for the search kernel");
+        if (us > spin_us)
+            std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return GSB_OK;
+}
+
+const char* device_error_text(uint32_t)
+{
+    return "the search kernel reported a failure (grid barrier or peer flag timed out, or a candidate buffer "
+           "overflowed); the workspace was reset";
+}
+
+// Results of enqueue_scan(slot, seq): waits for every shard's record and merges them.
+int collect_scan(const gsb_db* db, uint32_t k, int slot, uint64_t seq, std::vector<unsigned long long>* keys,
+                 uint64_t* survivors)
+{
     keys->clear();
     *survivors = 0;
+    bool failed = false;
     for (size_t i = 0; i < db->shards.size(); i++) {
-        const Shard& sh = db->shards[i];
+        Shard& sh = const_cast<Shard&>(db->shards[i]);
         if (sh.n_rows == 0)
             continue;
-        GSB_CUDA(cudaSetDevice(sh.device));
-        GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
-        const uint32_t n = *reinterpret_cast<const uint32_t*>(sh.ws.out_host + k + 1);
-        *survivors += sh.ws.out_host[k];
+        const unsigned long long* rec = sh.ws.slots[slot].host;
+        int rc = wait_word(rec + k + 2, seq, sh.ws.stream);
+        if (rc)
+            return rc;
+        const uint32_t n = *reinterpret_cast<const uint32_t*>(rec + k + 1);
+        if (n == gsb::kCountError) {
+            failed = true;
+            ws_recover(sh);
+            continue;
+        }
+        *survivors += rec[k];
         if (db->shards.size() == 1) {
-            keys->assign(sh.ws.out_host, sh.ws.out_host + n);
+            keys->assign(rec, rec + n);
         } else {
             // merge of per-shard sorted lists on the host (reference .cu:366 sorts on the host too)
             const size_t old = keys->size();
-            keys->insert(keys->end(), sh.ws.out_host, sh.ws.out_host + n);
-            std::inplace_merge(keys->begin(), keys->begin() + old, keys->end(),
-                               std::greater<unsigned long long>());
+            keys->insert(keys->end(), rec, rec + n);
+            std::inplace_merge(keys->begin(), keys->begin() + old, keys->end(), std::greater<unsigned long long>());
             if (keys->size() > k)
                 keys->resize(k);
         }
     }
+    if (failed)
+        return fail(GSB_ERR_CUDA, device_error_text(0));
     return GSB_OK;
+}
+
+int scan_all_shards(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, float cutoff,
+                    unsigned long long key_ceiling, std::vector<unsigned long long>* keys, uint64_t* survivors)
+{
+    const uint64_t seq = ++db->done_seq;
+    int rc = enqueue_scan(db, q_dev_words, k, cutoff, key_ceiling, kSyncSlot, seq);
+    if (rc)
+        return rc;
+    return collect_scan(db, k, kSyncSlot, seq, keys, survivors);
 }
 
 // Largest k one fused launch can select on every shard of this database.
@@ -666,13 +959,14 @@ enum BatchKernel { kBatchNone = 0, kBatchPopc = 1, kBatchSliced = 2 };
 BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, float cutoff)
 {
     const int mode = env_int("GSB_BATCH_KERNEL", 1);
-    if (mode == 0 || !db->layout.rowpop || db->layout.dev_words > 32 || db->fold_factor != 1 || k < 1 ||
-        k > gsb::kMaxBatchK || n_queries < 2)
+    if (mode == 0 || !db->layout.rowpop || db->layout.dev_words > 32 || k < 1 || k > gsb::kMaxBatchK || n_queries < 2)
         return kBatchNone;
     if (mode == 2)
         return kBatchPopc;
-    if (mode == 3)
+    if (mode == 3 && db->metric == gsb::kMetricTanimoto)
         return kBatchSliced;
+    if (db->metric != gsb::kMetricTanimoto)
+        return kBatchPopc; // the bit-sliced kernel's filter bound is Tanimoto's
     // The bit-sliced kernel pays a transposition per tile: measured cross-over between 4 and 8
     // queries (profiles/r01_sweep.md).  (A low positive cutoff sends many rows through its exact
     // path, but even with every row on that path it stays ahead of the POPC kernel.)
@@ -836,6 +1130,10 @@ void fill_batch_params(const gsb_db* db, const Shard& sh, uint32_t nq, uint32_t 
     p.out_keys = out_keys;
     p.out_n = out_n;
     p.out_survivors = out_surv;
+    p.spin_timeout_ns = 10ull * spin_timeout_ns(); // CTAs finish far apart in the multi-query kernels
+    p.metric = db->metric;
+    p.alpha = db->alpha;
+    p.beta = db->beta;
 }
 
 // Bit-sliced kernel over one shard (gsb_sliced.cuh): query lists, then one pass.  Everything is
@@ -867,6 +1165,9 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         return rc;
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
+    rc = gate_launch(sh.device, ws, st, grid); // before anything of this pass touches the workspace
+    if (rc)
+        return rc;
     gsb::sliced_build_lists_kernel<<<1, gsb::kMaxSlicedQueries, 0, st>>>(d_queries, nq, dev_words, ws.slists, ws.slofs,
                                                                          ws.sngrp, ws.spopq, ws.smeta);
     g_launches++;
@@ -928,22 +1229,33 @@ int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, BatchKernel
     fill_batch_params(db, sh, nq, k, cutoff, d_queries, out_keys, out_n, out_surv, &p);
     p.stages = plan.stages;
     GSB_CUDA(cudaSetDevice(sh.device));
+    rc = gate_launch(sh.device, sh.ws, st, plan.grid);
+    if (rc)
+        return rc;
     return launch_batch(db->layout, p, plan, st);
 }
 
+void to_dev_words(const gsb_db* db, const int32_t* query, std::vector<uint32_t>* out);
+
 // Host-buffer batch over every shard: groups of up to batch_max_queries(which) queries per pass.
-int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t* query_words, int n_queries, uint32_t k,
-                             float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+// merged[q] receives the best k_scan keys of query q over all shards, approx[q] its survivor count.
+int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t* query_words, int n_queries,
+                             uint32_t k_scan, float cutoff, std::vector<std::vector<unsigned long long>>* merged_out,
+                             std::vector<uint64_t>* approx_out)
 {
     const Layout& l = db->layout;
-    const uint32_t words = db->words;
+    const uint32_t words = db->words, k = k_scan;
     const int group = static_cast<int>(batch_max_queries(which));
+    merged_out->assign(n_queries, {});
+    approx_out->assign(n_queries, 0);
+    std::vector<uint32_t> one;
     for (int q0 = 0; q0 < n_queries; q0 += group) {
         const uint32_t nq = static_cast<uint32_t>(std::min<int>(group, n_queries - q0));
         std::vector<uint32_t> padded(static_cast<size_t>(nq) * l.dev_words, 0u);
-        for (uint32_t j = 0; j < nq; j++)
-            std::memcpy(padded.data() + static_cast<size_t>(j) * l.dev_words,
-                        query_words + static_cast<size_t>(q0 + j) * words, words * 4);
+        for (uint32_t j = 0; j < nq; j++) { // zero padded to the device width, folded like the rows
+            to_dev_words(db, query_words + static_cast<size_t>(q0 + j) * words, &one);
+            std::memcpy(padded.data() + static_cast<size_t>(j) * l.dev_words, one.data(), l.dev_words * 4);
+        }
         for (size_t i = 0; i < db->shards.size(); i++) {
             Shard& sh = const_cast<Shard&>(db->shards[i]);
             if (sh.n_rows == 0)
@@ -956,6 +1268,9 @@ int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t*
             if (rc)
                 return rc;
             GSB_CUDA(cudaSetDevice(sh.device));
+            rc = gate_launch(sh.device, sh.ws, sh.ws.stream, 0); // the copy below already touches the workspace
+            if (rc)
+                return rc;
             GSB_CUDA(cudaMemcpyAsync(sh.ws.bqueries, padded.data(), padded.size() * 4, cudaMemcpyHostToDevice,
                                      sh.ws.stream));
             unsigned long long* keys = sh.ws.bout;
@@ -967,10 +1282,9 @@ int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t*
             GSB_CUDA(cudaMemcpyAsync(sh.ws.bout_host, sh.ws.bout, (static_cast<size_t>(nq) * (k + 2ull)) * 8,
                                      cudaMemcpyDeviceToHost, sh.ws.stream));
         }
-        std::vector<std::vector<unsigned long long>> merged(nq);
-        std::vector<uint64_t> approx(nq, 0);
+        bool failed = false;
         for (size_t i = 0; i < db->shards.size(); i++) {
-            const Shard& sh = db->shards[i];
+            Shard& sh = const_cast<Shard&>(db->shards[i]);
             if (sh.n_rows == 0)
                 continue;
             GSB_CUDA(cudaSetDevice(sh.device));
@@ -979,26 +1293,23 @@ int search_batch_kernel_path(const gsb_db* db, BatchKernel which, const int32_t*
             const unsigned long long* surv = keys + static_cast<size_t>(nq) * k;
             const uint32_t* cnt = reinterpret_cast<const uint32_t*>(surv + nq);
             for (uint32_t j = 0; j < nq; j++) {
-                approx[j] += surv[j];
-                auto& m = merged[j];
+                if (cnt[j] == gsb::kCountError) {
+                    failed = true;
+                    break;
+                }
+                (*approx_out)[q0 + j] += surv[j];
+                auto& m = (*merged_out)[q0 + j];
                 const size_t old = m.size();
                 m.insert(m.end(), keys + static_cast<size_t>(j) * k, keys + static_cast<size_t>(j) * k + cnt[j]);
                 std::inplace_merge(m.begin(), m.begin() + old, m.end(), std::greater<unsigned long long>());
                 if (m.size() > k)
                     m.resize(k);
             }
+            if (failed)
+                ws_recover(sh);
         }
-        for (uint32_t j = 0; j < nq; j++) {
-            const size_t q = static_cast<size_t>(q0) + j;
-            for (size_t i = 0; i < merged[j].size(); i++) {
-                const Cand c = decode(merged[j][i]);
-                out_rows[q * k + i] = c.row;
-                out_scores[q * k + i] = c.score;
-            }
-            out_n[q] = static_cast<uint32_t>(merged[j].size());
-            if (out_approx)
-                out_approx[q] = approx[j];
-        }
+        if (failed)
+            return fail(GSB_ERR_CUDA, device_error_text(0));
     }
     return GSB_OK;
 }
@@ -1013,15 +1324,130 @@ void to_dev_words(const gsb_db* db, const int32_t* query, std::vector<uint32_t>*
     }
 }
 
-float score_cpu(const uint32_t* q, const uint32_t* d, uint32_t words)
+// Host twin of the kernels' epilogue (gsb::similarity): reference calculation_functors.cpp:8-19 /
+// fingerprintdb_cuda.cu:387-399 for Tanimoto; Dice and Tversky as defined in gsb_kernels.cuh (f32,
+// every operation rounded — this file is compiled with -ffp-contract=off).
+float score_cpu(const gsb_db* db, const uint32_t* q, const uint32_t* d, uint32_t words)
 {
-    // reference calculation_functors.cpp:8-19 / fingerprintdb_cuda.cu:387-399
-    int total = 0, common = 0;
+    int pq = 0, pd = 0, common = 0;
     for (uint32_t i = 0; i < words; i++) {
-        total += __builtin_popcount(q[i]) + __builtin_popcount(d[i]);
+        pq += __builtin_popcount(q[i]);
+        pd += __builtin_popcount(d[i]);
         common += __builtin_popcount(q[i] & d[i]);
     }
-    return static_cast<float>(common) / static_cast<float>(total - common);
+    if (db->metric == gsb::kMetricTanimoto)
+        return static_cast<float>(common) / static_cast<float>(pq + pd - common);
+    if (db->metric == gsb::kMetricDice)
+        return static_cast<float>(2 * common) / static_cast<float>(pq + pd);
+    const float c = static_cast<float>(common);
+    const float t1 = db->alpha * static_cast<float>(pq - common);
+    const float t2 = db->beta * static_cast<float>(pd - common);
+    const float den = (t1 + t2) + c;
+    return c / den;
+}
+
+// ---- folded search, second stage on the device ------------------------------------------------
+void unregister_host_rows(gsb_db* db)
+{
+    if (db->host_registered)
+        for (auto& hc : db->host)
+            cudaHostUnregister(hc.bytes.data());
+    db->host_registered = false;
+    if (db->d_chunks)
+        cudaFree(db->d_chunks);
+    db->d_chunks = nullptr;
+    if (db->rescore_host)
+        cudaFreeHost(db->rescore_host);
+    db->rescore_host = db->rescore_dev = nullptr;
+    db->rescore_cap = 0;
+    cudaGetLastError();
+}
+
+// Page-lock and map the unfolded host chunks so that the re-score kernel can read candidate rows
+// in place.  Failure is not an error (the re-score then runs on the host, as in the reference).
+void register_host_rows(gsb_db* db)
+{
+    if (db->host_registered || db->host.empty() || db->shards.empty() || env_int("GSB_FOLD_RESCORE_HOST", 0))
+        return;
+    cudaSetDevice(db->shards[0].device);
+    std::vector<gsb::RescoreChunk> table;
+    size_t done = 0;
+    bool ok = true;
+    for (auto& hc : db->host) {
+        if (cudaHostRegister(hc.bytes.data(), hc.bytes.size(), cudaHostRegisterPortable | cudaHostRegisterMapped) !=
+            cudaSuccess) {
+            ok = false;
+            break;
+        }
+        done++;
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, hc.bytes.data(), 0) != cudaSuccess) {
+            ok = false;
+            break;
+        }
+        table.push_back({static_cast<const uint32_t*>(d), hc.row0, hc.n_rows});
+    }
+    if (ok && cudaMalloc(&db->d_chunks, table.size() * sizeof(gsb::RescoreChunk)) == cudaSuccess &&
+        cudaMemcpy(db->d_chunks, table.data(), table.size() * sizeof(gsb::RescoreChunk), cudaMemcpyHostToDevice) ==
+            cudaSuccess) {
+        db->host_registered = true;
+        return;
+    }
+    for (size_t i = 0; i < done; i++)
+        cudaHostUnregister(db->host[i].bytes.data());
+    cudaGetLastError();
+    std::fprintf(stderr, "[gpusim_b200] could not map the host rows for the device re-score; folded searches "
+                         "re-score on the host\n");
+}
+
+// keys: candidates of the folded scan in canonical order.  On return keys holds, best first, the
+// re-scored keys ((score bits + 1) << 32 | 0xFFFFFFFF - candidate index; high word 0 = NaN).
+int rescore_on_device(gsb_db* db, const uint32_t* qfull, const std::vector<unsigned long long>& cand,
+                      std::vector<unsigned long long>* out)
+{
+    const size_t n = cand.size();
+    out->clear();
+    if (n == 0)
+        return GSB_OK;
+    Shard& sh = db->shards[0];
+    GSB_CUDA(cudaSetDevice(sh.device));
+    if (2 * n + 1 > db->rescore_cap) {
+        if (db->rescore_host) {
+            GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+            GSB_CUDA(cudaFreeHost(db->rescore_host));
+        }
+        db->rescore_host = db->rescore_dev = nullptr;
+        db->rescore_cap = 0;
+        const size_t cap = 2 * static_cast<size_t>(pow2ceil(n)) + 1;
+        void* h = nullptr;
+        void* d = nullptr;
+        GSB_CUDA(cudaHostAlloc(&h, cap * 8, cudaHostAllocMapped | cudaHostAllocPortable));
+        GSB_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+        db->rescore_host = static_cast<unsigned long long*>(h);
+        db->rescore_dev = static_cast<unsigned long long*>(d);
+        db->rescore_cap = cap;
+    }
+    std::memcpy(db->rescore_host, cand.data(), n * 8);
+    gsb::RescoreParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.cand = db->rescore_dev;
+    p.out = db->rescore_dev + n;
+    p.n = static_cast<uint32_t>(n);
+    p.words = db->words;
+    p.n_chunks = static_cast<uint32_t>(db->host.size());
+    p.chunks = db->d_chunks;
+    p.metric = db->metric;
+    p.alpha = db->alpha;
+    p.beta = db->beta;
+    std::memcpy(p.q, qfull, db->words * 4);
+    const unsigned blocks = static_cast<unsigned>((n * 32 + 255) / 256);
+    gsb::rescore_kernel<<<blocks, 256, 0, sh.ws.stream>>>(p);
+    g_launches++;
+    GSB_CUDA(cudaGetLastError());
+    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+    out->assign(db->rescore_host + n, db->rescore_host + 2 * n);
+    std::sort(out->begin(), out->end(), std::greater<unsigned long long>());
+    return GSB_OK;
 }
 
 int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<uint32_t>* out);
@@ -1131,18 +1557,21 @@ int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, in
     return gsb_db_create_adopt(std::move(chunks), fp_bits, fp_count, out);
 }
 
-int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base, uint64_t seed,
-                            uint32_t plant_period, gsb_db** out)
+int gsb_db_create_synthetic_sharded(const int* devices, int n_devices, int fp_bits, uint64_t n_rows,
+                                    uint64_t row_base, uint64_t seed, uint32_t plant_period, gsb_db** out)
 {
-    if (!out)
+    GSB_TRY
+    if (!out || !devices || n_devices < 1)
         return fail(GSB_ERR_INVALID, "null argument");
     if (fp_bits <= 0 || fp_bits % 32 != 0 || fp_bits / 32 > GSB_MAX_WORDS)
         return fail(GSB_ERR_INVALID, "fp_bitcount must be a multiple of 32 in [32, 4096]");
     if (row_base + n_rows > 0xffffffffull)
         return fail(GSB_ERR_INVALID, "row ids must fit 32 bits");
-    if (device < 0 || device >= gsb_device_count())
-        return fail(GSB_ERR_CUDA, "no such CUDA device");
-    std::unique_ptr<gsb_db> db(new gsb_db);
+    for (int i = 0; i < n_devices; i++)
+        if (devices[i] < 0 || devices[i] >= gsb_device_count())
+            return fail(GSB_ERR_CUDA, "no such CUDA device");
+    // (unique_ptr with a destroying deleter: a failure half way releases the shards made so far)
+    std::unique_ptr<gsb_db, void (*)(gsb_db*)> db(new gsb_db, gsb_db_destroy);
     db->fp_bits = fp_bits;
     db->words = fp_bits / 32;
     db->count = n_rows;
@@ -1152,42 +1581,56 @@ int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t r
         return rc;
     if (db->layout.dev_words != db->words)
         return fail(GSB_ERR_INVALID, "synthetic shards need a power-of-two word count >= 4");
-    db->shards.resize(1);
-    Shard& sh = db->shards[0];
-    sh.device = device;
-    sh.row_base = row_base;
-    sh.n_rows = n_rows;
-    rc = ws_init(sh);
-    if (rc)
-        return rc;
     const Layout& l = db->layout;
-    sh.n_tiles = static_cast<uint32_t>((n_rows + l.tile_rows - 1) / l.tile_rows);
-    sh.bytes = padded_tile_bytes(l, sh.n_tiles);
-    if (gsb_device_free_bytes(device) <= sh.bytes)
-        return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
-    GSB_CUDA(cudaSetDevice(device));
-    GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
-    GSB_CUDA(cudaMemsetAsync(sh.tiles, 0, sh.bytes, sh.ws.stream)); // padding batches must read as empty rows
-    const uint64_t n_words = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows * l.dev_words;
-    if (n_words) {
-        const uint64_t blocks = (n_words + 255) / 256;
-        if (blocks > 0x7fffffffull)
-            return fail(GSB_ERR_INVALID, "shard too large");
-        gsb::synth_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, sh.ws.stream>>>(
-            sh.tiles, n_rows, row_base, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words, seed, plant_period);
-        g_launches++;
-        if (l.rowpop) {
-            const uint64_t rows = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows;
-            gsb::tile_popcount_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, sh.ws.stream>>>(
-                sh.tiles, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words);
+    const uint64_t per = (n_rows + n_devices - 1) / n_devices;
+    db->shards.resize(n_devices);
+    for (int i = 0; i < n_devices; i++) { // contiguous, equal row ranges; generation runs on all devices at once
+        Shard& sh = db->shards[i];
+        sh.device = devices[i];
+        const uint64_t off = std::min<uint64_t>(n_rows, static_cast<uint64_t>(i) * per);
+        sh.row_base = row_base + off;
+        sh.n_rows = std::min<uint64_t>(n_rows - off, per);
+        rc = ws_init(sh);
+        if (rc)
+            return rc;
+        sh.n_tiles = static_cast<uint32_t>((sh.n_rows + l.tile_rows - 1) / l.tile_rows);
+        sh.bytes = padded_tile_bytes(l, sh.n_tiles);
+        if (gsb_device_free_bytes(sh.device) <= sh.bytes)
+            return fail(GSB_ERR_NOMEM, "Can't find a GPU with enough memory to copy data.");
+        GSB_CUDA(cudaSetDevice(sh.device));
+        GSB_CUDA(cudaMalloc(&sh.tiles, sh.bytes));
+        GSB_CUDA(cudaMemsetAsync(sh.tiles, 0, sh.bytes, sh.ws.stream)); // padding batches must read as empty rows
+        const uint64_t n_words = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows * l.dev_words;
+        if (n_words) {
+            const uint64_t blocks = (n_words + 255) / 256;
+            if (blocks > 0x7fffffffull)
+                return fail(GSB_ERR_INVALID, "shard too large");
+            gsb::synth_fill_kernel<<<static_cast<unsigned>(blocks), 256, 0, sh.ws.stream>>>(
+                sh.tiles, sh.n_rows, sh.row_base, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words, seed, plant_period);
             g_launches++;
+            if (l.rowpop) {
+                const uint64_t rows = static_cast<uint64_t>(sh.n_tiles) * l.tile_rows;
+                gsb::tile_popcount_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, sh.ws.stream>>>(
+                    sh.tiles, sh.n_tiles, l.tile_rows, l.tile_stride, l.dev_words);
+                g_launches++;
+            }
         }
     }
-    GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
-    GSB_CUDA(cudaGetLastError());
+    for (Shard& sh : db->shards) {
+        GSB_CUDA(cudaSetDevice(sh.device));
+        GSB_CUDA(cudaStreamSynchronize(sh.ws.stream));
+        GSB_CUDA(cudaGetLastError());
+    }
     db->uploaded = true;
     *out = db.release();
     return GSB_OK;
+    GSB_CATCH
+}
+
+int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base, uint64_t seed,
+                            uint32_t plant_period, gsb_db** out)
+{
+    return gsb_db_create_synthetic_sharded(&device, 1, fp_bits, n_rows, row_base, seed, plant_period, out);
 }
 
 int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_factor)
@@ -1204,6 +1647,9 @@ int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_f
         ws_free(sh);
     db->shards.clear();
     db->uploaded = false;
+    for (auto& pd : db->pending)
+        pd.ticket = 0;
+    unregister_host_rows(db);
     // reference fingerprintdb_cuda.cu:170-173
     unsigned f = std::max(1u, fold_factor);
     while (db->words % f != 0)
@@ -1245,6 +1691,8 @@ int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_f
         if (rc)
             return rc;
     }
+    if (f > 1) // second stage of folded searches reads the full rows in place (mapped host memory)
+        register_host_rows(db);
     db->uploaded = true;
     return GSB_OK;
 }
@@ -1253,6 +1701,7 @@ void gsb_db_destroy(gsb_db* db)
 {
     if (!db)
         return;
+    unregister_host_rows(db);
     for (auto& sh : db->shards)
         ws_free(sh);
     delete db;
@@ -1282,36 +1731,28 @@ int gsb_db_get_fingerprint(const gsb_db* db, uint64_t row, int32_t* out_words)
     return GSB_OK;
 }
 
-int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k, float cutoff,
-                  uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+} // extern "C"
+
+namespace
 {
-    if (!db || !query_words || !out_n || (k > 0 && (!out_rows || !out_scores)))
-        return fail(GSB_ERR_INVALID, "null argument");
-    if (n_words != static_cast<int>(db->words))
-        return fail(GSB_ERR_INVALID, "query width does not match the database");
-    if (gsb_device_count() == 0)
-        return fail(GSB_ERR_CUDA, "no CUDA device: the GPU search path has no CPU fallback");
-    if (!db->uploaded)
-        return fail(GSB_ERR_STATE, "database is not on the GPU: call gsb_db_upload first");
-    std::lock_guard<std::mutex> lock(db->mu);
-    std::vector<uint32_t> q;
-    to_dev_words(db, query_words, &q);
+// reference .cu:284-287: candidates to pull back from the (folded) scan
+uint64_t scan_candidates(const gsb_db* db, uint32_t k)
+{
     const unsigned f = db->fold_factor;
-    // reference .cu:284-287: candidates to pull back from the (folded) scan
     uint64_t k_scan = k;
     if (f > 1)
         k_scan = static_cast<uint64_t>(k) * f * static_cast<uint64_t>(std::log2(2.0 * f));
-    k_scan = std::min<uint64_t>(k_scan, db->count);
-    std::vector<unsigned long long> keys;
-    uint64_t survivors = 0;
-    int rc = scan_topk(db, q.data(), std::max<uint64_t>(k_scan, 1), cutoff, &keys, &survivors);
-    if (rc)
-        return rc;
-    if (keys.size() > k_scan)
-        keys.resize(k_scan);
-    if (out_approx)
-        *out_approx = survivors;
-    if (f == 1) {
+    return std::min<uint64_t>(k_scan, db->count);
+}
+
+// Canonical keys of the scan -> caller's arrays.  Unfolded: decode.  Folded: second stage, the
+// candidates are scored again with their full fingerprints (reference .cu:307-331), ordered by the
+// new score (stable over the candidate order == top_results_bubble_sort, .cpp:92-103), cut to k and
+// at the first score below the cutoff (:323-326).
+int finish_search(const gsb_db* db, const int32_t* query_words, uint32_t k, float cutoff,
+                  std::vector<unsigned long long>& keys, uint32_t* out_rows, float* out_scores, uint32_t* out_n)
+{
+    if (db->fold_factor == 1) {
         const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(keys.size(), k));
         for (uint32_t i = 0; i < n; i++) {
             const Cand c = decode(keys[i]);
@@ -1321,17 +1762,29 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
         *out_n = n;
         return GSB_OK;
     }
-    // folded: re-score the candidates with the full fingerprints (reference .cu:307-331)
-    std::vector<Cand> cand(keys.size());
     const uint32_t* qfull = reinterpret_cast<const uint32_t*>(query_words);
-    for (size_t i = 0; i < keys.size(); i++) {
-        cand[i].row = decode(keys[i]).row;
-        cand[i].score = score_cpu(qfull, db->host_row(cand[i].row), db->words);
+    std::vector<Cand> cand(keys.size());
+    if (db->host_registered) {
+        std::vector<unsigned long long> rescored;
+        int rc = rescore_on_device(const_cast<gsb_db*>(db), qfull, keys, &rescored);
+        if (rc)
+            return rc;
+        for (size_t i = 0; i < rescored.size(); i++) {
+            const uint32_t idx = 0xffffffffu - static_cast<uint32_t>(rescored[i] & 0xffffffffu);
+            const uint32_t hi = static_cast<uint32_t>(rescored[i] >> 32);
+            const uint32_t bits = hi ? hi - 1u : 0x7fc00000u;
+            cand[i].row = decode(keys[idx]).row;
+            std::memcpy(&cand[i].score, &bits, 4);
+        }
+    } else {
+        for (size_t i = 0; i < keys.size(); i++) {
+            cand[i].row = decode(keys[i]).row;
+            cand[i].score = score_cpu(db, qfull, db->host_row(cand[i].row), db->words);
+        }
+        auto nan_last = [](float sc) { return sc != sc ? -1.0f : sc; };
+        std::stable_sort(cand.begin(), cand.end(),
+                         [&](const Cand& a, const Cand& b) { return nan_last(a.score) > nan_last(b.score); });
     }
-    // top_results_bubble_sort (.cpp:92-103) == stable descending sort of the candidate order
-    auto nan_last = [](float s) { return s != s ? -1.0f : s; };
-    std::stable_sort(cand.begin(), cand.end(),
-                     [&](const Cand& a, const Cand& b) { return nan_last(a.score) > nan_last(b.score); });
     uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(cand.size(), k));
     for (uint32_t i = 0; i < n; i++) {
         if (cand[i].score < cutoff) { // .cu:323-326
@@ -1345,28 +1798,203 @@ int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uin
     return GSB_OK;
 }
 
+int check_search_args(const gsb_db* db, const int32_t* query_words, int n_words)
+{
+    if (!db || !query_words)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (n_words != static_cast<int>(db->words))
+        return fail(GSB_ERR_INVALID, "query width does not match the database");
+    if (gsb_device_count() == 0)
+        return fail(GSB_ERR_CUDA, "no CUDA device: the GPU search path has no CPU fallback");
+    if (!db->uploaded)
+        return fail(GSB_ERR_STATE, "database is not on the GPU: call gsb_db_upload first");
+    return GSB_OK;
+}
+
+// One launch serves the query (unfolded rows and a k the in-kernel select can hold)?
+bool one_launch_query(const gsb_db* db, uint32_t k)
+{
+    if (db->fold_factor != 1 || k == 0)
+        return false;
+    Plan probe;
+    for (const Shard& sh : db->shards)
+        if (sh.n_rows && make_plan(db->layout, sh, k, &probe) != GSB_OK)
+            return false;
+    return true;
+}
+
+int search_sync_locked(const gsb_db* db, const int32_t* query_words, uint32_t k, float cutoff, uint32_t* out_rows,
+                       float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+{
+    std::vector<uint32_t> q;
+    to_dev_words(db, query_words, &q);
+    const uint64_t k_scan = scan_candidates(db, k);
+    std::vector<unsigned long long> keys;
+    uint64_t survivors = 0;
+    int rc = scan_topk(db, q.data(), std::max<uint64_t>(k_scan, 1), cutoff, &keys, &survivors);
+    if (rc)
+        return rc;
+    if (keys.size() > k_scan)
+        keys.resize(k_scan);
+    if (out_approx)
+        *out_approx = survivors;
+    return finish_search(db, query_words, k, cutoff, keys, out_rows, out_scores, out_n);
+}
+} // namespace
+
+extern "C" {
+
+int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k, float cutoff,
+                  uint32_t* out_rows, float* out_scores, uint32_t* out_n, uint64_t* out_approx)
+{
+    GSB_TRY
+    if (!out_n || (k > 0 && (!out_rows || !out_scores)))
+        return fail(GSB_ERR_INVALID, "null argument");
+    int rc = check_search_args(db, query_words, n_words);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    return search_sync_locked(db, query_words, k, cutoff, out_rows, out_scores, out_n, out_approx);
+    GSB_CATCH
+}
+
+int gsb_db_search_async(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k, float cutoff,
+                        uint64_t* ticket)
+{
+    GSB_TRY
+    if (!ticket)
+        return fail(GSB_ERR_INVALID, "null argument");
+    int rc = check_search_args(db, query_words, n_words);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    const uint64_t t = db->next_ticket;
+    gsb_db::Pending& pd = db->pending[t % kAsyncDepth];
+    if (pd.ticket != 0)
+        return fail(GSB_ERR_STATE, "too many searches in flight: wait for ticket " + std::to_string(pd.ticket) + " first");
+    pd.k = k;
+    pd.cutoff = cutoff;
+    pd.deferred = !one_launch_query(db, k);
+    pd.query.assign(query_words, query_words + n_words);
+    if (!pd.deferred) {
+        std::vector<uint32_t> q;
+        to_dev_words(db, query_words, &q);
+        pd.seq = ++db->done_seq;
+        rc = enqueue_scan(db, q.data(), k, cutoff, ~0ull, static_cast<int>(t % kAsyncDepth), pd.seq);
+        if (rc)
+            return rc;
+    }
+    pd.ticket = t;
+    db->next_ticket++;
+    *ticket = t;
+    return GSB_OK;
+    GSB_CATCH
+}
+
+int gsb_db_search_wait(const gsb_db* db, uint64_t ticket, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
+                       uint64_t* out_approx)
+{
+    GSB_TRY
+    if (!db || !out_n || ticket == 0)
+        return fail(GSB_ERR_INVALID, "null argument");
+    gsb_db::Pending& pd = db->pending[ticket % kAsyncDepth];
+    gsb_db::Pending mine;
+    {
+        std::lock_guard<std::mutex> lock(db->mu);
+        if (pd.ticket != ticket)
+            return fail(GSB_ERR_STATE, "no such search in flight");
+        mine = pd;
+    }
+    if (mine.k > 0 && (!out_rows || !out_scores))
+        return fail(GSB_ERR_INVALID, "null argument");
+    int rc;
+    if (mine.deferred) { // folded rows / very large k: several launches, done here
+        std::lock_guard<std::mutex> lock(db->mu);
+        rc = search_sync_locked(db, mine.query.data(), mine.k, mine.cutoff, out_rows, out_scores, out_n, out_approx);
+    } else {
+        // the record is this ticket's until the slot is released below: no lock while waiting
+        std::vector<unsigned long long> keys;
+        uint64_t survivors = 0;
+        rc = collect_scan(db, mine.k, static_cast<int>(ticket % kAsyncDepth), mine.seq, &keys, &survivors);
+        if (rc == GSB_OK) {
+            if (out_approx)
+                *out_approx = survivors;
+            rc = finish_search(db, mine.query.data(), mine.k, mine.cutoff, keys, out_rows, out_scores, out_n);
+        }
+    }
+    std::lock_guard<std::mutex> lock(db->mu);
+    pd.ticket = 0;
+    return rc;
+    GSB_CATCH
+}
+
 int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words, int n_queries, uint32_t k,
                         float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
                         uint64_t* out_approx)
 {
+    GSB_TRY
     if (n_queries < 0)
         return fail(GSB_ERR_INVALID, "negative query count");
-    if (db && query_words && out_rows && out_scores && out_n && db->uploaded &&
-        n_words == static_cast<int>(db->words)) {
-        const BatchKernel which = batch_kernel_choice(db, k, n_queries, cutoff);
-        if (which != kBatchNone) {
-            std::lock_guard<std::mutex> lock(db->mu);
-            return search_batch_kernel_path(db, which, query_words, n_queries, k, cutoff, out_rows, out_scores, out_n,
-                                            out_approx);
+    if (n_queries == 0)
+        return GSB_OK;
+    if (!out_n || (k > 0 && (!out_rows || !out_scores)))
+        return fail(GSB_ERR_INVALID, "null argument");
+    int rc = check_search_args(db, query_words, n_words);
+    if (rc)
+        return rc;
+    std::lock_guard<std::mutex> lock(db->mu);
+    // folded rows: the scan pulls k * F * floor(log2 2F) candidates per query (reference .cu:284-287)
+    const uint64_t k_scan = db->fold_factor == 1 ? k : scan_candidates(db, k);
+    const BatchKernel which =
+        k_scan <= gsb::kMaxBatchK ? batch_kernel_choice(db, static_cast<uint32_t>(k_scan), n_queries, cutoff) : kBatchNone;
+    if (which != kBatchNone) {
+        std::vector<std::vector<unsigned long long>> merged;
+        std::vector<uint64_t> approx;
+        rc = search_batch_kernel_path(db, which, query_words, n_queries, static_cast<uint32_t>(k_scan), cutoff, &merged,
+                                      &approx);
+        if (rc)
+            return rc;
+        for (int qi = 0; qi < n_queries; qi++) {
+            rc = finish_search(db, query_words + static_cast<size_t>(qi) * n_words, k, cutoff, merged[qi],
+                               out_rows + static_cast<size_t>(qi) * k, out_scores + static_cast<size_t>(qi) * k, out_n + qi);
+            if (rc)
+                return rc;
+            if (out_approx)
+                out_approx[qi] = approx[qi];
         }
+        return GSB_OK;
+    }
+    // No multi-query kernel for this shape (rows wider than 1024 bits, more than 512 candidates per
+    // query, plain layout): one scan per query.  gsb_db_batch_mode() tells callers beforehand.
+    if (n_queries >= 8) {
+        static std::atomic<bool> warned{false};
+        if (!warned.exchange(true))
+            std::fprintf(stderr, "[gpusim_b200] gsb_db_search_batch: no multi-query kernel for this database / k; "
+                                 "%d queries run as %d single-query scans (see gsb_db_batch_mode)\n", n_queries, n_queries);
     }
     for (int qi = 0; qi < n_queries; qi++) {
-        int rc = gsb_db_search(db, query_words + static_cast<size_t>(qi) * n_words, n_words, k, cutoff,
-                               out_rows + static_cast<size_t>(qi) * k, out_scores + static_cast<size_t>(qi) * k,
-                               out_n + qi, out_approx ? out_approx + qi : nullptr);
+        rc = search_sync_locked(db, query_words + static_cast<size_t>(qi) * n_words, k, cutoff,
+                                out_rows + static_cast<size_t>(qi) * k, out_scores + static_cast<size_t>(qi) * k, out_n + qi,
+                                out_approx ? out_approx + qi : nullptr);
         if (rc)
             return rc;
     }
+    return GSB_OK;
+    GSB_CATCH
+}
+
+int gsb_db_batch_mode(const gsb_db* db, uint32_t k, int n_queries, float cutoff, int* mode, uint32_t* queries_per_pass)
+{
+    if (!db || !mode)
+        return fail(GSB_ERR_INVALID, "null argument");
+    if (!db->uploaded)
+        return fail(GSB_ERR_STATE, "the device layout is chosen at upload: call gsb_db_upload first");
+    const uint64_t k_scan = db->fold_factor == 1 ? k : scan_candidates(db, k);
+    const BatchKernel which =
+        k_scan <= gsb::kMaxBatchK ? batch_kernel_choice(db, static_cast<uint32_t>(k_scan), n_queries, cutoff) : kBatchNone;
+    *mode = which == kBatchSliced ? GSB_BATCH_SLICED : (which == kBatchPopc ? GSB_BATCH_POPC : GSB_BATCH_LOOPED);
+    if (queries_per_pass)
+        *queries_per_pass = which == kBatchNone ? 1u : batch_max_queries(which);
     return GSB_OK;
 }
 
@@ -1388,7 +2016,7 @@ int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words,
         float* out = sp + hc.row0;
         parallel_for(hc.n_rows, [=](uint64_t lo, uint64_t hi) {
             for (uint64_t r = lo; r < hi; r++)
-                out[r] = score_cpu(q, rows + r * words, words);
+                out[r] = score_cpu(db, q, rows + r * words, words);
         });
     }
     const uint32_t n = static_cast<uint32_t>(std::min<uint64_t>(k, db->count));
@@ -1412,11 +2040,20 @@ int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words,
     return GSB_OK;
 }
 
-int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k, float cutoff,
-                         gsb_key* d_out_keys, uint32_t* d_out_n, uint64_t* d_out_survivors)
+int gsb_db_search_enqueue(const gsb_db* db, void* stream, const int32_t* h_query, const int32_t* d_query,
+                          uint32_t flags, uint32_t k, float cutoff, const gsb_exchange* xchg, const gsb_sink* sink)
 {
-    if (!db || !d_query || !d_out_keys || !d_out_n || !d_out_survivors || k == 0)
+    GSB_TRY
+    if (!db || (!h_query && !d_query) || !sink || !sink->n || !sink->approx || k == 0)
         return fail(GSB_ERR_INVALID, "null argument");
+    if (xchg) {
+        if (!sink->rows || !sink->scores)
+            return fail(GSB_ERR_INVALID, "a fused search needs sink rows and scores");
+        if (xchg->world < 2 || xchg->world > gsb::kMaxRanks || xchg->rank >= xchg->world || xchg->seq == 0)
+            return fail(GSB_ERR_INVALID, "bad exchange descriptor");
+    } else if (!sink->keys) {
+        return fail(GSB_ERR_INVALID, "a shard-local search needs sink keys");
+    }
     if (!db->uploaded || db->shards.size() != 1)
         return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
     if (db->fold_factor != 1)
@@ -1427,17 +2064,86 @@ int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query,
     int rc = make_plan(db->layout, sh, k, &plan);
     if (rc)
         return rc;
-    rc = ws_reserve(sh, k, plan.grid, false);
+    rc = ws_reserve(sh, k, plan.grid, -1);
     if (rc)
         return rc;
     GSB_CUDA(cudaSetDevice(sh.device));
     gsb::ScanParams p;
     fill_params(db, sh, plan, k, cutoff, &p);
-    p.q_dev = reinterpret_cast<const uint32_t*>(d_query);
-    p.out_keys = reinterpret_cast<unsigned long long*>(d_out_keys);
-    p.out_n = d_out_n;
-    p.out_survivors = reinterpret_cast<unsigned long long*>(d_out_survivors);
-    return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
+    if (h_query) { // travels as a kernel parameter
+        std::vector<uint32_t> q;
+        to_dev_words(db, h_query, &q);
+        std::memcpy(p.q_host, q.data(), db->layout.dev_words * 4);
+    } else {
+        p.q_dev = reinterpret_cast<const uint32_t*>(d_query);
+        p.early_wait = (flags & GSB_QUERY_STABLE) ? 0u : 1u;
+    }
+    p.out_n = sink->n;
+    p.out_survivors = reinterpret_cast<unsigned long long*>(sink->approx);
+    p.out_done = reinterpret_cast<unsigned long long*>(sink->done);
+    p.out_done_value = sink->done_value;
+    if (xchg) {
+        p.out_rows = sink->rows;
+        p.out_scores = sink->scores;
+        p.x_world = xchg->world;
+        p.x_rank = xchg->rank;
+        p.x_seq = xchg->seq;
+        for (uint32_t r = 0; r < xchg->world; r++)
+            p.x_peer[r] = xchg->peer_base[r];
+    } else {
+        p.out_keys = reinterpret_cast<unsigned long long*>(sink->keys);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    rc = gate_launch(sh.device, sh.ws, st, plan.grid);
+    if (rc)
+        return rc;
+    return launch_scan(db->layout, p, plan, st);
+    GSB_CATCH
+}
+
+int gsb_db_search_device(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k, float cutoff,
+                         gsb_key* d_out_keys, uint32_t* d_out_n, uint64_t* d_out_survivors)
+{
+    if (!d_query || !d_out_keys || !d_out_n || !d_out_survivors)
+        return fail(GSB_ERR_INVALID, "null argument");
+    gsb_sink sink;
+    std::memset(&sink, 0, sizeof(sink));
+    sink.keys = d_out_keys;
+    sink.n = d_out_n;
+    sink.approx = d_out_survivors;
+    return gsb_db_search_enqueue(db, stream, nullptr, d_query, 0, k, cutoff, nullptr, &sink);
+}
+
+int gsb_wait_word(const uint64_t* word, uint64_t value, uint64_t timeout_us)
+{
+    if (!word)
+        return fail(GSB_ERR_INVALID, "null argument");
+    const volatile uint64_t* w = word;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint64_t spins = 1; *w != value; spins++) {
+        GSB_CPU_RELAX();
+        if ((spins & 0xfff) == 0 && timeout_us &&
+            static_cast<uint64_t>(std::chrono::duration_cast<std::chrono::microseconds>(
+                                      std::chrono::steady_clock::now() - t0).count()) > timeout_us)
+            return fail(GSB_ERR_CUDA, "timed out waiting for a completion word");
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    return GSB_OK;
+}
+
+int gsb_db_set_metric(gsb_db* db, int metric, float alpha, float beta)
+{
+    if (!db)
+        return fail(GSB_ERR_INVALID, "null database");
+    if (metric != GSB_METRIC_TANIMOTO && metric != GSB_METRIC_DICE && metric != GSB_METRIC_TVERSKY)
+        return fail(GSB_ERR_INVALID, "unknown metric");
+    if (metric == GSB_METRIC_TVERSKY && !(alpha >= 0.0f && beta >= 0.0f))
+        return fail(GSB_ERR_INVALID, "Tversky weights must be >= 0");
+    std::lock_guard<std::mutex> lock(db->mu);
+    db->metric = static_cast<uint32_t>(metric);
+    db->alpha = metric == GSB_METRIC_TVERSKY ? alpha : 1.0f;
+    db->beta = metric == GSB_METRIC_TVERSKY ? beta : 1.0f;
+    return GSB_OK;
 }
 
 int gsb_db_search_batch_device(const gsb_db* db, void* stream, const int32_t* d_queries, int n_queries, uint32_t k,
@@ -1506,37 +2212,15 @@ int gsb_db_search_device_fused(const gsb_db* db, void* stream, const int32_t* d_
                                const gsb_exchange* xchg, uint32_t* d_out_rows, float* d_out_scores,
                                uint32_t* d_out_n, uint64_t* d_out_approx)
 {
-    if (!db || !d_query || !xchg || !d_out_rows || !d_out_scores || !d_out_n || !d_out_approx || k == 0)
+    if (!d_query || !xchg || !d_out_rows || !d_out_scores || !d_out_n || !d_out_approx)
         return fail(GSB_ERR_INVALID, "null argument");
-    if (xchg->world < 2 || xchg->world > gsb::kMaxRanks || xchg->rank >= xchg->world || xchg->seq == 0)
-        return fail(GSB_ERR_INVALID, "bad exchange descriptor");
-    if (!db->uploaded || db->shards.size() != 1)
-        return fail(GSB_ERR_STATE, "device search needs exactly one uploaded shard in this process");
-    if (db->fold_factor != 1)
-        return fail(GSB_ERR_STATE, "device search does not re-score folded databases");
-    std::lock_guard<std::mutex> lock(db->mu);
-    Shard& sh = const_cast<Shard&>(db->shards[0]);
-    Plan plan;
-    int rc = make_plan(db->layout, sh, k, &plan);
-    if (rc)
-        return rc;
-    rc = ws_reserve(sh, k, plan.grid, false);
-    if (rc)
-        return rc;
-    GSB_CUDA(cudaSetDevice(sh.device));
-    gsb::ScanParams p;
-    fill_params(db, sh, plan, k, cutoff, &p);
-    p.q_dev = reinterpret_cast<const uint32_t*>(d_query);
-    p.out_n = d_out_n;
-    p.out_survivors = reinterpret_cast<unsigned long long*>(d_out_approx);
-    p.out_rows = d_out_rows;
-    p.out_scores = d_out_scores;
-    p.x_world = xchg->world;
-    p.x_rank = xchg->rank;
-    p.x_seq = xchg->seq;
-    for (uint32_t r = 0; r < xchg->world; r++)
-        p.x_peer[r] = xchg->peer_base[r];
-    return launch_scan(db->layout, p, plan, static_cast<cudaStream_t>(stream));
+    gsb_sink sink;
+    std::memset(&sink, 0, sizeof(sink));
+    sink.rows = d_out_rows;
+    sink.scores = d_out_scores;
+    sink.n = d_out_n;
+    sink.approx = d_out_approx;
+    return gsb_db_search_enqueue(db, stream, nullptr, d_query, 0, k, cutoff, xchg, &sink);
 }
 
 int gsb_merge_device(int device, void* stream, const gsb_key* d_keys, const uint32_t* d_counts, int n_lists,

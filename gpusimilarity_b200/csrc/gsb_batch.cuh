@@ -28,7 +28,7 @@ struct BatchCtrl {
     unsigned int ticket;      // CTAs that finished scanning + sorting their lists
     unsigned int next_batch;  // dynamic work distribution
     unsigned int done;        // CTAs that finished their merges (last one resets the block)
-    unsigned int pad;
+    unsigned int error;       // kErr* bits raised by any CTA (reported through out_n, then cleared)
 };
 
 struct BatchParams {
@@ -47,6 +47,9 @@ struct BatchParams {
     unsigned long long* out_keys;       // [nq][k]
     uint32_t* out_n;                    // [nq]
     unsigned long long* out_survivors;  // [nq]
+    unsigned long long spin_timeout_ns; // wall-clock bound of the grid-wide arrival spin
+    uint32_t metric;                    // kMetric* (the bit-sliced kernel's filter knows Tanimoto only)
+    float alpha, beta;
 };
 
 // Cut back every candidate list of this CTA that is more than half full (or, with exact_all, cut
@@ -113,11 +116,16 @@ __device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigne
     cta_sync<NT>();
     // ---- grid-wide arrival (the grid is persistent: one CTA per SM, all resident)
     if (tid == 0) {
+        if (*cs.error)
+            atomicOr(&p.ctrl->error, *cs.error);
         atomicAdd(&p.ctrl->ticket, 1u);
-        const long long t0 = clock64();
+        const unsigned long long t0 = global_ns();
         while (*reinterpret_cast<volatile unsigned int*>(&p.ctrl->ticket) < gridDim.x) {
-            if (clock64() - t0 > (200ll << 30)) // ~100 s (CTAs finish far apart here); fail loudly, never hang
-                __trap();
+            // (CTAs finish far apart here: the host passes ten times the single-query bound)
+            if (global_ns() - t0 > p.spin_timeout_ns) { // not co-resident: report it, never hang or trap
+                atomicOr(&p.ctrl->error, kErrGridBarrier);
+                break;
+            }
         }
         __threadfence();
     }
@@ -130,7 +138,8 @@ __device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigne
         for (uint32_t i = tid; i < p.k; i += NT)
             p.out_keys[(uint64_t) j * p.k + i] = i < n ? cs.buf[i] : 0ull;
         if (tid == 0) {
-            p.out_n[j] = n;
+            const unsigned int err = *cs.error | *reinterpret_cast<volatile unsigned int*>(&p.ctrl->error);
+            p.out_n[j] = err ? kCountError : n;
             p.out_survivors[j] = drop_zero ? *reinterpret_cast<volatile unsigned long long*>(&p.surv_acc[j]) : p.n_rows;
         }
         cta_sync<NT>();
@@ -149,6 +158,7 @@ __device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigne
         if (tid == 0) {
             p.ctrl->next_batch = 0;
             p.ctrl->done = 0;
+            p.ctrl->error = 0;
             __threadfence();
             p.ctrl->ticket = 0;
         }
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     __shared__ __align__(8) uint64_t s_full[CW * kMaxStages];
     __shared__ uint32_t s_bid[CW * kMaxStages];
     __shared__ unsigned long long s_stage_tau;
-    __shared__ unsigned int s_stage_count, s_epoch_req, s_done, s_alive, s_dummy_epoch;
+    __shared__ unsigned int s_stage_count, s_epoch_req, s_done, s_alive, s_dummy_epoch, s_error;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t S = p.stages, nq = p.nq;
@@ -197,6 +207,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     cs.tau = &s_stage_tau;
     cs.epoch_req = &s_dummy_epoch;
     cs.hist = s_hist;
+    cs.error = &s_error;
     unsigned long long* my_cand = p.cand + (uint64_t) blockIdx.x * nq * kBatchListCap;
     const uint32_t high_water = kBatchListCap - 32u * CW - 64u;
 
@@ -211,6 +222,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
         s_epoch_req = 0;
         s_done = 0;
         s_alive = 0;
+        s_error = 0;
     }
     if (lane == 0) {
         for (uint32_t s = 0; s < S; s++)
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
             for (int i = 0; i < L; i++)
                 v[i] = __popc(d[i].x & q.x) + __popc(d[i].y & q.y) + __popc(d[i].z & q.z) + __popc(d[i].w & q.w);
             const uint32_t common = transpose_reduce<L>(v, lane);
-            float score = tanimoto_div(common, s_popq[j] + popd - common);
+            float score = similarity(p.metric, p.alpha, p.beta, common, s_popq[j], popd);
             score = (score >= p.cutoff) ? score : 0.0f; // reference .cu:102
             const bool survivor = valid && (!drop_zero || score != 0.0f);
             if (drop_zero) {
@@ -327,9 +339,10 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (pass) {
                     const unsigned idx = base + __popc(m & ((1u << lane) - 1u));
-                    if (idx >= kBatchListCap)
-                        __trap();
-                    my_cand[(uint64_t) j * kBatchListCap + idx] = key;
+                    if (idx < kBatchListCap)
+                        my_cand[(uint64_t) j * kBatchListCap + idx] = key;
+                    else
+                        atomicOr(&s_error, kErrOverflow);
                 }
             }
         }
@@ -364,7 +377,7 @@ merge_batch_kernel(const unsigned long long* records, uint32_t n_ranks, uint32_t
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ unsigned long long s_tau;
-    __shared__ unsigned int s_count, s_epoch_req, s_alive;
+    __shared__ unsigned int s_count, s_epoch_req, s_alive, s_error;
     CandShared cs;
     cs.buf = reinterpret_cast<unsigned long long*>(smem);
     cs.cap = cap;
@@ -372,7 +385,10 @@ merge_batch_kernel(const unsigned long long* records, uint32_t n_ranks, uint32_t
     cs.tau = &s_tau;
     cs.epoch_req = &s_epoch_req;
     cs.hist = reinterpret_cast<unsigned int*>(cs.buf + cap);
+    cs.error = &s_error;
     const uint32_t tid = threadIdx.x, j = blockIdx.x;
+    if (tid == 0)
+        s_error = 0;
     const uint64_t rec_len = (uint64_t) nq * (k + 2);
     merge_lists<kMergeThreads>(cs, records + (uint64_t) j * k, nullptr, n_ranks, static_cast<uint32_t>(rec_len), k, 0ull,
                                &s_alive, tid);
@@ -386,7 +402,7 @@ merge_batch_kernel(const unsigned long long* records, uint32_t n_ranks, uint32_t
         unsigned long long total = 0;
         for (uint32_t r = 0; r < n_ranks; r++)
             total += records[r * rec_len + (uint64_t) nq * k + j];
-        out_n[j] = n;
+        out_n[j] = s_error ? kCountError : n;
         out_approx[j] = total;
     }
 }

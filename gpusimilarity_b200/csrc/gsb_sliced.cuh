@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_full[CW];
     __shared__ unsigned long long s_stage_tau;
-    __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_next_q, s_need_select;
+    __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_next_q, s_need_select, s_error;
     __shared__ unsigned int s_claim[3]; // tile claims of this, the next and the next-but-one iteration
     __shared__ float s_pdmin[kSlicedTileBatches]; // smallest row popcount of each batch of the tile
 
@@ -218,6 +218,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     cs.tau = &s_stage_tau;
     cs.epoch_req = &s_dummy_epoch;
     cs.hist = reinterpret_cast<unsigned int*>(tile + (size_t) kBatchListCap * 8);
+    cs.error = &s_error;
     unsigned long long* my_cand = p.cand + (uint64_t) blockIdx.x * nq * kBatchListCap;
 
     const bool drop_zero = p.cutoff > 0.0f; // reference .cu:265
@@ -247,6 +248,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     if (tid == 0) {
         s_alive = 0;
         s_need_select = 0;
+        s_error = 0;
         // claims below n_mini are the mini tiles, one per CTA and handed out statically (every CTA
         // warms up on its own); the tiles proper are claimed dynamically, two iterations ahead
         s_claim[0] = blockIdx.x < sp.n_mini ? blockIdx.x : sp.n_mini + atomicAdd(&p.ctrl->next_batch, 1u);
@@ -343,9 +345,10 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
                 base = __shfl_sync(kFull, base, 0);
                 if (pass) {
                     const unsigned idx = base + __popc(pm & ((1u << lane) - 1u));
-                    if (idx >= kBatchListCap)
-                        __trap(); // unreachable: lists are cut to <= 1024 entries between tiles
-                    my_cand[(uint64_t) j * kBatchListCap + idx] = key;
+                    if (idx < kBatchListCap) // (lists are cut to <= 1024 entries between tiles)
+                        my_cand[(uint64_t) j * kBatchListCap + idx] = key;
+                    else
+                        atomicOr(&s_error, kErrOverflow);
                     // every candidate is counted once in the grid-wide score histogram of its query
                     const uint32_t bucket = sliced_bucket(__float_as_uint(score));
                     const unsigned peers = __match_any_sync(pm, bucket);

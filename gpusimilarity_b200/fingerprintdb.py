@@ -86,6 +86,25 @@ class FingerprintDB:
         self.m_dbkey, self.m_smiles, self.m_ids = dbkey, [], []
         return self
 
+    @classmethod
+    def synthetic_sharded(cls, n_rows: int, devices: Sequence[int], fp_bitcount: int = 1024, row_base: int = 0,
+                          seed: int = 0x5EED5EED, plant_period: int = 0, dbkey: str = "pass") -> "FingerprintDB":
+        """The same synthetic rows as contiguous, equal shards over ``devices``, driven by this ONE
+        process (the reference's own multi-GPU mode, fingerprintdb_cuda.cu:176-183)."""
+        self = cls.__new__(cls)
+        self._h = C.c_void_p()
+        arr = (C.c_int * len(devices))(*devices)
+        check(lib().gsb_db_create_synthetic_sharded(arr, len(devices), fp_bitcount, n_rows, row_base, seed,
+                                                    plant_period, C.byref(self._h)))
+        self.m_dbkey, self.m_smiles, self.m_ids = dbkey, [], []
+        return self
+
+    def setMetric(self, metric: str = "tanimoto", alpha: float = 1.0, beta: float = 1.0) -> None:
+        """Similarity metric of later searches: 'tanimoto' (the reference's), 'dice', 'tversky'."""
+        code = {"tanimoto": _lib.GSB_METRIC_TANIMOTO, "dice": _lib.GSB_METRIC_DICE,
+                "tversky": _lib.GSB_METRIC_TVERSKY}[metric]
+        check(lib().gsb_db_set_metric(self._h, code, alpha, beta))
+
     # -- life cycle ---------------------------------------------------------------------
     def copyToGPU(self, fold_factor: int = 1, devices: Optional[Sequence[int]] = None) -> None:
         if devices:
@@ -150,6 +169,33 @@ class FingerprintDB:
                                   rows.ctypes.data, scores.ctypes.data, C.byref(n), C.byref(approx)))
         return rows[:n.value].astype(np.int64), scores[:n.value].copy(), int(approx.value)
 
+    def search_rows_async(self, query, max_return_count: int, similarity_cutoff: float) -> int:
+        """Queue one search (gsb_db_search_async); returns the ticket for ``search_rows_wait``.  Up to
+        four searches per database may be in flight; consecutive ones overlap on the device."""
+        q = _as_i32(query)
+        ticket = C.c_uint64(0)
+        check(lib().gsb_db_search_async(self._h, q.ctypes.data, q.shape[0], int(max_return_count), similarity_cutoff,
+                                        C.byref(ticket)))
+        self._pending_k = getattr(self, "_pending_k", {})
+        self._pending_k[ticket.value] = int(max_return_count)
+        return ticket.value
+
+    def search_rows_wait(self, ticket: int) -> Tuple[np.ndarray, np.ndarray, int]:
+        k = self._pending_k.pop(ticket)
+        rows = np.empty(max(k, 1), dtype=np.uint32)
+        scores = np.empty(max(k, 1), dtype=np.float32)
+        n, approx = C.c_uint32(0), C.c_uint64(0)
+        check(lib().gsb_db_search_wait(self._h, ticket, rows.ctypes.data, scores.ctypes.data, C.byref(n),
+                                       C.byref(approx)))
+        return rows[:n.value].astype(np.int64), scores[:n.value].copy(), int(approx.value)
+
+    def batch_mode(self, max_return_count: int, n_queries: int, similarity_cutoff: float = 0.0) -> Tuple[int, int]:
+        """(GSB_BATCH_* mode, queries per pass) gsb_db_search_batch would use."""
+        mode, per = C.c_int(0), C.c_uint32(0)
+        check(lib().gsb_db_batch_mode(self._h, int(max_return_count), n_queries, similarity_cutoff, C.byref(mode),
+                                      C.byref(per)))
+        return mode.value, per.value
+
     def search(self, query, dbkey: str, max_return_count: int, similarity_cutoff: float,
                results_smiles: list, results_ids: list, results_scores: list) -> Optional[int]:
         """reference FingerprintDB::search (.cu:341-381): results are APPENDED to the three lists;
@@ -175,6 +221,20 @@ class FingerprintDB:
                                         rows.ctypes.data, scores.ctypes.data, n.ctypes.data,
                                         approx.ctypes.data))
         return [(rows[i, :n[i]].astype(np.int64), scores[i, :n[i]].copy(), int(approx[i])) for i in range(nq)]
+
+    def search_batch_rows_raw(self, queries, max_return_count: int, similarity_cutoff: float):
+        """gsb_db_search_batch with the result arrays as they come: (rows [nq][k] int64, scores [nq][k],
+        n [nq], approx [nq])."""
+        q = np.ascontiguousarray(queries, dtype=np.int32)
+        nq, k = q.shape[0], int(max_return_count)
+        rows = np.zeros((nq, max(k, 1)), dtype=np.uint32)
+        scores = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        n = np.zeros(nq, dtype=np.uint32)
+        approx = np.zeros(nq, dtype=np.uint64)
+        check(lib().gsb_db_search_batch(self._h, q.ctypes.data, q.shape[1], nq, k, similarity_cutoff,
+                                        rows.ctypes.data, scores.ctypes.data, n.ctypes.data,
+                                        approx.ctypes.data))
+        return rows.astype(np.int64), scores, n, approx
 
     def search_cpu_rows(self, query, max_return_count: int) -> Tuple[np.ndarray, np.ndarray]:
         q = _as_i32(query)

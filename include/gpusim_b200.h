@@ -37,6 +37,20 @@ extern "C" {
 
 #define GSB_MAX_WORDS 128   /* widest fingerprint: 4096 bits */
 
+/* similarity metrics (gsb_db_set_metric); every kernel shares the scan, only the epilogue differs */
+#define GSB_METRIC_TANIMOTO 0 /* c / (pq + pd - c)   reference fingerprintdb_cuda.cu:89-103 (default) */
+#define GSB_METRIC_DICE 1     /* 2c / (pq + pd)                                                      */
+#define GSB_METRIC_TVERSKY 2  /* c / (alpha (pq - c) + beta (pd - c) + c), f32, every op rounded      */
+
+/* how gsb_db_search_batch serves a batch (gsb_db_batch_mode) */
+#define GSB_BATCH_LOOPED 0    /* one single-query scan per query                                      */
+#define GSB_BATCH_POPC 1      /* up to 256 queries per pass over the database (POPC kernel)           */
+#define GSB_BATCH_SLICED 2    /* up to 1024 queries per pass (bit-sliced kernel)                      */
+
+/* *n of a device-side result when the launch failed without killing the context (a grid barrier
+ * or peer flag timed out): the host-buffer entry points turn it into GSB_ERR_CUDA */
+#define GSB_COUNT_ERROR 0xffffffffu
+
 typedef struct gsb_db gsb_db;
 
 /* ---- library / devices -------------------------------------------------------------- */
@@ -65,12 +79,19 @@ int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, in
  * DESIGN.md ("Synthetic data"; host twin: oracle/oracle.py synth_rows).  Already uploaded. */
 int gsb_db_create_synthetic(int device, int fp_bits, uint64_t n_rows, uint64_t row_base,
                             uint64_t seed, uint32_t plant_period, gsb_db** out);
+/* The same rows split into contiguous, equal shards over `devices` (one process driving several
+ * GPUs, the reference's own mode, .cu:176-183); a device may be listed more than once. */
+int gsb_db_create_synthetic_sharded(const int* devices, int n_devices, int fp_bits, uint64_t n_rows,
+                                    uint64_t row_base, uint64_t seed, uint32_t plant_period, gsb_db** out);
 /* reference FingerprintDB::copyToGPU, .cu:168-195.  Rows are split into contiguous, equal
  * shards over `devices` (NULL / 0 = every visible device that is needed).  fold_factor is
  * bumped to the next divisor of the word count (.cu:170-173); with fold_factor > 1 the
  * folded rows are what is uploaded and searched (re-scored with the full rows kept on the host). */
 int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_factor);
 void gsb_db_destroy(gsb_db* db);
+/* Similarity metric of every later search of this database (GSB_METRIC_*; alpha / beta are the
+ * Tversky weights, ignored otherwise).  The reference scores Tanimoto only; SURVEY §8 f4. */
+int gsb_db_set_metric(gsb_db* db, int metric, float alpha, float beta);
 
 uint64_t gsb_db_count(const gsb_db* db);          /* FingerprintDB::count(), .h:74            */
 int gsb_db_fp_bits(const gsb_db* db);             /* getFingerprintBitcount(), .h:124-127      */
@@ -89,16 +110,34 @@ int gsb_db_get_fingerprint(const gsb_db* db, uint64_t row, int32_t* out_words);
 int gsb_db_search(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k,
                   float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
                   uint64_t* out_approx);
+/* The same search split in two, so that a caller can keep several queries in flight (up to 4 per
+ * database): _async queues the launch(es) and returns a ticket at once, _wait blocks until that
+ * query's results are on the host and hands them out.  The query travels as a kernel parameter and
+ * the last CTA of the launch stores the results straight into mapped pinned host memory, so there
+ * is no cudaMemcpy and no stream synchronize on the path; consecutive queries overlap on the device
+ * (programmatic dependent launch: the scan of query i+1 starts while the last CTA of query i is
+ * still sorting).  gsb_db_search is _async followed by _wait. */
+int gsb_db_search_async(const gsb_db* db, const int32_t* query_words, int n_words, uint32_t k,
+                        float cutoff, uint64_t* ticket);
+int gsb_db_search_wait(const gsb_db* db, uint64_t ticket, uint32_t* out_rows, float* out_scores,
+                       uint32_t* out_n, uint64_t* out_approx);
 /* New (the reference serves one query per request, gpusim.cpp:407-414): n_queries queries
  * over the same database; query q's results land at out_rows + q*k etc.  Identical results to
  * n_queries calls of gsb_db_search.  With the default layout, rows of at most 1024 bits, no fold
  * and k <= 512 the queries share ONE pass over the database per group: 1024 queries per pass
- * with the bit-sliced kernel (6 or more queries; gsb_sliced.cuh), 256 with the POPC kernel;
- * otherwise they are searched one after the other.
+ * with the bit-sliced kernel (6 or more queries; gsb_sliced.cuh), 256 with the POPC kernel.
+ * Folded databases take the same path as long as k * F * floor(log2 2F) <= 512 candidates per
+ * query (second stage on the device).  Otherwise the queries are searched one after the other;
+ * gsb_db_batch_mode says beforehand which of the three it will be (and a batch of 8 or more
+ * queries that ends up looping says so once on stderr).
  * GSB_BATCH_KERNEL=0/2/3 forces looping / the POPC kernel / the bit-sliced kernel. */
 int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_words,
                         int n_queries, uint32_t k, float cutoff, uint32_t* out_rows,
                         float* out_scores, uint32_t* out_n, uint64_t* out_approx);
+/* *mode = GSB_BATCH_* that gsb_db_search_batch would use for this k / batch size / cutoff,
+ * *queries_per_pass (may be NULL) the queries sharing one pass over the database. */
+int gsb_db_batch_mode(const gsb_db* db, uint32_t k, int n_queries, float cutoff, int* mode,
+                      uint32_t* queries_per_pass);
 /* reference FingerprintDB::search_cpu, fingerprintdb_cuda.cpp:20-54: host threads, CPU
  * scores (no cutoff, 0/0 = NaN), first k in stable score-descending order.  A separate
  * entry point of the reference API — never used as a fallback by gsb_db_search.
@@ -111,7 +150,13 @@ int gsb_db_search_cpu(const gsb_db* db, const int32_t* query_words, int n_words,
  * better in canonical order, so one unsigned compare orders candidates. */
 typedef uint64_t gsb_key;
 
-/* Asynchronous search of this process's single shard on `stream` (a cudaStream_t; NULL = the
+/* All searches of one gsb_db share its per-shard workspace.  Launches on ONE stream are ordered by
+ * the stream (and overlap head-to-tail through programmatic dependent launch); a launch that
+ * arrives on ANOTHER stream than the work still in flight is made to wait for it with an event, so
+ * callers need no synchronisation of their own.  A stream handed to these entry points must stay
+ * valid until the next search of the database (or its destruction).
+ *
+ * Asynchronous search of this process's single shard on `stream` (a cudaStream_t; NULL = the
  * legacy default stream).  d_query: fp_bits/32 words in device memory.  d_out_keys: k keys,
  * sorted best first, unused tail zero-filled; d_out_n: entries written; d_out_survivors: this
  * shard's approximate count.  All three live in device memory.  One launch, no host sync. */
@@ -160,6 +205,32 @@ int gsb_exchange_bytes(uint32_t world, uint32_t k, uint64_t* bytes);
 int gsb_db_search_device_fused(const gsb_db* db, void* stream, const int32_t* d_query, uint32_t k,
                                float cutoff, const gsb_exchange* xchg, uint32_t* d_out_rows,
                                float* d_out_scores, uint32_t* d_out_n, uint64_t* d_out_approx);
+
+/* The general form of the two device entry points above.  The query comes from host memory
+ * (h_query: copied into the launch parameters, no H2D copy) or device memory (d_query; pass
+ * GSB_QUERY_STABLE when nothing queued on the stream after the previous search writes it, which
+ * lets the launch overlap that search's tail — without the flag the kernel first waits for the
+ * work before it).  xchg == NULL: shard-local search (sink.keys / n / approx).  xchg != NULL: fused
+ * cross-GPU search (sink.rows / scores / n / approx).  Every sink pointer must be device
+ * accessible: device memory, or pinned host memory — then the results land on the host without any
+ * copy, and `done` (optional) is set to done_value after everything else is visible system-wide:
+ * poll it with gsb_wait_word instead of synchronising the stream. */
+#define GSB_QUERY_STABLE 1u
+typedef struct gsb_sink {
+    gsb_key* keys;
+    uint32_t* rows;
+    float* scores;
+    uint32_t* n;       /* entries written, or GSB_COUNT_ERROR */
+    uint64_t* approx;
+    uint64_t* done;
+    uint64_t done_value;
+} gsb_sink;
+int gsb_db_search_enqueue(const gsb_db* db, void* stream, const int32_t* h_query, const int32_t* d_query,
+                          uint32_t flags, uint32_t k, float cutoff, const gsb_exchange* xchg,
+                          const gsb_sink* sink);
+/* Spin until *word == value (a completion word in pinned host memory); timeout_us = 0 waits for
+ * ever.  GSB_ERR_CUDA on timeout. */
+int gsb_wait_word(const uint64_t* word, uint64_t value, uint64_t timeout_us);
 
 /* ---- .fsim ingest without Qt (reference GPUSimServer::extractData, gpusim.cpp:173-253, and the
  * Decompress*Runnable helpers :48-85): big-endian QDataStream framing, qUncompress = zlib after a

@@ -58,6 +58,48 @@ def tanimoto_scores_gpu(query: np.ndarray, db: np.ndarray, cutoff: float) -> np.
         return np.where(s >= c, s, np.float32(0)).astype(np.float32)
 
 
+def metric_scores_gpu(query: np.ndarray, db: np.ndarray, cutoff: float, metric: str = "tanimoto",
+                      alpha: float = 1.0, beta: float = 1.0) -> np.ndarray:
+    """Dice and Tversky variants of the scan.  The reference scores Tanimoto only, so
+    these have no reference counterpart to be pinned to ("parity unpinned" for the two extra
+    metrics): this function IS their definition, restated operation by operation by the kernels
+    (gsb_kernels.cuh metric_score) — f32, every operation rounded, then the reference's cutoff rule
+    (fingerprintdb_cuda.cu:102).
+      dice      f32(2c) / f32(pq + pd)
+      tversky   f32(c) / ((alpha * f32(pq - c) + beta * f32(pd - c)) + f32(c))"""
+    if metric == "tanimoto":
+        return tanimoto_scores_gpu(query, db, cutoff)
+    q = _u32(query).reshape(1, -1)
+    d = _u32(db)
+    c = np.bitwise_count(d & q).sum(axis=1, dtype=np.int64)
+    pq = int(np.bitwise_count(q).sum())
+    pd = popcounts(d)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        if metric == "dice":
+            s = (2 * c).astype(np.float32) / (pq + pd).astype(np.float32)
+        elif metric == "tversky":
+            c32 = c.astype(np.float32)
+            t1 = np.float32(alpha) * (pq - c).astype(np.float32)
+            t2 = np.float32(beta) * (pd - c).astype(np.float32)
+            s = c32 / ((t1 + t2) + c32)
+        else:
+            raise ValueError(metric)
+        return np.where(s >= np.float32(cutoff), s, np.float32(0)).astype(np.float32)
+
+
+def search_gpu_metric(query: np.ndarray, db: np.ndarray, k: int, cutoff: float, metric: str,
+                      alpha: float = 1.0, beta: float = 1.0) -> Tuple[np.ndarray, np.ndarray, int]:
+    """search_gpu with the score of ``metric_scores_gpu`` (same cutoff / survivor / order rules)."""
+    s = metric_scores_gpu(query, db, cutoff, metric, alpha, beta)
+    rows = np.arange(db.shape[0], dtype=np.int64)
+    if np.float32(cutoff) > 0:
+        keep = s != 0
+        s, rows = s[keep], rows[keep]
+    approx = int(rows.shape[0])
+    order = canonical_order(s, rows)[:k]
+    return rows[order], s[order], approx
+
+
 def canonical_order(scores: np.ndarray, rows: np.ndarray) -> np.ndarray:
     """Indices that sort by (score desc, row asc) — the order a stable descending sort of
     (score, row) produces from ascending rows (fingerprintdb_cuda.cu:245,280-282)."""

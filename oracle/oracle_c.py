@@ -42,6 +42,14 @@ def oracle_lib():
         lib.oracle_synth_rows.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32,
                                           C.c_void_p, C.c_int]
         lib.oracle_synth_rows.restype = None
+        lib.oracle_stream_search.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint64,
+                                             C.c_uint64, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_int]
+        lib.oracle_stream_search.restype = None
+        lib.oracle_stream_search_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint64,
+                                                   C.c_uint64, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_int]
+        lib.oracle_stream_search_multi.restype = None
         _oracle = lib
     return _oracle
 
@@ -77,6 +85,36 @@ def c_synth_db(seed: int, n_rows: int, words: int = 32, plant_period: int = 0, r
     oracle_lib().oracle_synth_rows(seed, n_rows, row_base, words, plant_period, out.ctypes.data,
                                    n_threads or (os.cpu_count() or 1))
     return out
+
+
+def c_stream_search(query, seed: int, plant_period: int, n_rows: int, k: int, cutoff: float,
+                    row_base: int = 0, n_threads: int = 0) -> Tuple[np.ndarray, np.ndarray, int]:
+    """oracle_search over rows [row_base, row_base + n_rows) of the synthetic database, generated on
+    the fly inside the scan (nothing is materialised): the full-size oracle for 1 B-row searches."""
+    q = _i32(query)
+    rows = np.empty(max(k, 1), dtype=np.uint32)
+    scores = np.empty(max(k, 1), dtype=np.float32)
+    n, approx = C.c_uint32(0), C.c_uint64(0)
+    oracle_lib().oracle_stream_search(q.ctypes.data, q.shape[0], seed, plant_period, n_rows, row_base, k,
+                                      cutoff, rows.ctypes.data, scores.ctypes.data, C.byref(n),
+                                      C.byref(approx), n_threads or (os.cpu_count() or 1))
+    return rows[:n.value].astype(np.int64), scores[:n.value], int(approx.value)
+
+
+def c_stream_search_multi(queries, seed: int, plant_period: int, n_rows: int, k: int, cutoff: float,
+                          row_base: int = 0, n_threads: int = 0):
+    """c_stream_search for a batch of queries in one pass over the generated rows.  Returns a list of
+    (rows, scores, approx), one per query."""
+    qs = np.ascontiguousarray(queries, dtype=np.int32)
+    nq = qs.shape[0]
+    rows = np.zeros((nq, max(k, 1)), dtype=np.uint32)
+    scores = np.zeros((nq, max(k, 1)), dtype=np.float32)
+    n = np.zeros(nq, dtype=np.uint32)
+    approx = np.zeros(nq, dtype=np.uint64)
+    oracle_lib().oracle_stream_search_multi(qs.ctypes.data, nq, qs.shape[1], seed, plant_period, n_rows, row_base, k,
+                                            cutoff, rows.ctypes.data, scores.ctypes.data, n.ctypes.data,
+                                            approx.ctypes.data, n_threads or (os.cpu_count() or 1))
+    return [(rows[i, :n[i]].astype(np.int64), scores[i, :n[i]].copy(), int(approx[i])) for i in range(nq)]
 
 
 def c_fold(fp, factor: int) -> np.ndarray:

@@ -263,3 +263,244 @@ void oracle_synth_rows(uint64_t seed, uint64_t n_rows, uint64_t row_base, int wo
         pthread_join(th[t], NULL);
     free(jobs); free(th);
 }
+
+/* ---- streamed search over the synthetic database: rows [row_base, row_base + n_rows) are generated
+ * on the fly (never materialised), scored and selected exactly like oracle_search.  Lets the tests
+ * check a 1 B-row GPU search (BASELINE configs[2]) bit for bit instead of by invariants. ---- */
+typedef struct {
+    const int32_t* q;
+    uint64_t seed, lo, hi, row_base;
+    int words;
+    uint32_t plant_period;
+    float cutoff;
+    heap_t heap;
+    uint64_t survivors;
+} stream_job_t;
+
+static void* stream_job(void* arg)
+{
+    stream_job_t* j = (stream_job_t*) arg;
+    const int drop_zero = j->cutoff > 0.0f;
+    uint32_t row[128], tmpl[128];
+    for (int w = 0; w < j->words; w++)
+        tmpl[w] = random_word(j->seed, SYNTH_TEMPLATE_ROW, (uint32_t) w);
+    for (uint64_t r = j->lo; r < j->hi; r++) {
+        const uint64_t grow = j->row_base + r;
+        int planted = j->plant_period > 0 && (hash32(j->seed, grow, 0, 7) % j->plant_period) == 0;
+        if (!planted) {
+            for (int w = 0; w < j->words; w++)
+                row[w] = random_word(j->seed, grow, (uint32_t) w);
+        } else {
+            memcpy(row, tmpl, (size_t) j->words * 4);
+            const uint32_t nflip = 1 + hash32(j->seed, grow, 1, 7) % SYNTH_MAX_FLIPS;
+            for (uint32_t f = 0; f < nflip; f++) {
+                const uint32_t pos = hash32(j->seed, grow, 2 + f, 7) % (uint32_t) (j->words * 32);
+                row[pos >> 5] ^= 1u << (pos & 31);
+            }
+        }
+        float s = score_row(j->q, (const int32_t*) row, j->words);
+        s = (s >= j->cutoff) ? s : 0.0f;
+        if (drop_zero && s == 0.0f)
+            continue;
+        j->survivors++;
+        cand_t c = {s, (uint32_t) grow};
+        heap_push(&j->heap, c);
+    }
+    return NULL;
+}
+
+void oracle_stream_search(const int32_t* query, int words, uint64_t seed, uint32_t plant_period,
+                          uint64_t n_rows, uint64_t row_base, uint32_t k, float cutoff,
+                          uint32_t* out_rows, float* out_scores, uint32_t* out_n,
+                          uint64_t* out_approx, int n_threads)
+{
+    if (n_threads < 1)
+        n_threads = 1;
+    stream_job_t* jobs = (stream_job_t*) calloc(n_threads, sizeof(stream_job_t));
+    pthread_t* th = (pthread_t*) calloc(n_threads, sizeof(pthread_t));
+    const uint64_t per = (n_rows + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        stream_job_t* j = &jobs[t];
+        j->q = query; j->seed = seed; j->row_base = row_base; j->words = words;
+        j->plant_period = plant_period; j->cutoff = cutoff;
+        j->lo = (uint64_t) t * per < n_rows ? (uint64_t) t * per : n_rows;
+        j->hi = j->lo + per < n_rows ? j->lo + per : n_rows;
+        j->heap.cap = k; j->heap.n = 0;
+        j->heap.h = k ? (cand_t*) malloc((size_t) k * sizeof(cand_t)) : NULL;
+        pthread_create(&th[t], NULL, stream_job, j);
+    }
+    uint64_t surv = 0;
+    uint32_t total = 0;
+    for (int t = 0; t < n_threads; t++) {
+        pthread_join(th[t], NULL);
+        surv += jobs[t].survivors;
+        total += jobs[t].heap.n;
+    }
+    cand_t* all = (cand_t*) malloc((size_t) (total ? total : 1) * sizeof(cand_t));
+    uint32_t o = 0;
+    for (int t = 0; t < n_threads; t++) {
+        memcpy(all + o, jobs[t].heap.h, (size_t) jobs[t].heap.n * sizeof(cand_t));
+        o += jobs[t].heap.n;
+        free(jobs[t].heap.h);
+    }
+    qsort(all, total, sizeof(cand_t), cmp_canonical);
+    const uint32_t n = total < k ? total : k;
+    for (uint32_t i = 0; i < n; i++) {
+        out_rows[i] = all[i].row;
+        out_scores[i] = all[i].score;
+    }
+    *out_n = n;
+    *out_approx = cutoff > 0.0f ? surv : n_rows;
+    free(all); free(jobs); free(th);
+}
+
+/* ---- the same for a batch of queries in ONE pass over the generated rows (row generation is the
+ * expensive part): out arrays are [nq][k]; bench.py checks BASELINE configs[4] (1024 queries,
+ * top-100) result lists and the single-query top-1000 against it at full size. ---- */
+typedef struct {
+    const int32_t* qs;
+    int nq;
+    uint64_t seed, lo, hi, row_base;
+    int words;
+    uint32_t plant_period;
+    float cutoff;
+    heap_t* heaps;      /* [nq] */
+    uint64_t* survivors; /* [nq] */
+} mstream_job_t;
+
+/* common[q] = popcount(query q AND row) for every query.  Cloned for CPUs with AVX-512 VPOPCNTDQ
+ * (the compiler vectorises the popcount reduction there); plain POPCNT elsewhere. */
+__attribute__((target_clones("arch=icelake-server", "default")))
+static void common_counts(const int32_t* qs, int nq, int words, const uint32_t* row, int* out)
+{
+    if ((words & 1) == 0) { /* popcount is additive: two 32-bit words at a time */
+        const int w64 = words / 2;
+        uint64_t r[64];
+        memcpy(r, row, (size_t) words * 4);
+        for (int q = 0; q < nq; q++) {
+            uint64_t a[64];
+            memcpy(a, qs + (size_t) q * words, (size_t) words * 4);
+            long long c = 0;
+            for (int w = 0; w < w64; w++)
+                c += __builtin_popcountll(a[w] & r[w]);
+            out[q] = (int) c;
+        }
+    } else {
+        for (int q = 0; q < nq; q++) {
+            const uint32_t* qw = (const uint32_t*) qs + (size_t) q * words;
+            int c = 0;
+            for (int w = 0; w < words; w++)
+                c += __builtin_popcount(qw[w] & row[w]);
+            out[q] = c;
+        }
+    }
+}
+
+static void* mstream_job(void* arg)
+{
+    mstream_job_t* j = (mstream_job_t*) arg;
+    const int drop_zero = j->cutoff > 0.0f;
+    const int words = j->words;
+    uint32_t row[128], tmpl[128];
+    int* popq = (int*) malloc((size_t) j->nq * sizeof(int));
+    int* commons = (int*) malloc((size_t) j->nq * sizeof(int));
+    for (int q = 0; q < j->nq; q++) {
+        popq[q] = 0;
+        for (int w = 0; w < words; w++)
+            popq[q] += __builtin_popcount((unsigned) j->qs[(size_t) q * words + w]);
+    }
+    for (int w = 0; w < words; w++)
+        tmpl[w] = random_word(j->seed, SYNTH_TEMPLATE_ROW, (uint32_t) w);
+    for (uint64_t r = j->lo; r < j->hi; r++) {
+        const uint64_t grow = j->row_base + r;
+        int planted = j->plant_period > 0 && (hash32(j->seed, grow, 0, 7) % j->plant_period) == 0;
+        if (!planted) {
+            for (int w = 0; w < words; w++)
+                row[w] = random_word(j->seed, grow, (uint32_t) w);
+        } else {
+            memcpy(row, tmpl, (size_t) words * 4);
+            const uint32_t nflip = 1 + hash32(j->seed, grow, 1, 7) % SYNTH_MAX_FLIPS;
+            for (uint32_t f = 0; f < nflip; f++) {
+                const uint32_t pos = hash32(j->seed, grow, 2 + f, 7) % (uint32_t) (words * 32);
+                row[pos >> 5] ^= 1u << (pos & 31);
+            }
+        }
+        int popd = 0;
+        for (int w = 0; w < words; w++)
+            popd += __builtin_popcount(row[w]);
+        common_counts(j->qs, j->nq, words, row, commons);
+        for (int q = 0; q < j->nq; q++) {
+            const int common = commons[q];
+            /* Cheap, conservative skip (no cutoff only): with the heap full, a row whose quotient is
+             * more than 0.1 % below the worst kept score cannot round up to it. */
+            heap_t* hp = &j->heaps[q];
+            if (!drop_zero && hp->n == hp->cap && hp->cap > 0 &&
+                (float) common < hp->h[0].score * (float) (popq[q] + popd - common) * 0.999f)
+                continue;
+            /* calculation_functors.cpp:18 with total = popq + popd */
+            float s = (float) common / (float) (popq[q] + popd - common);
+            s = (s >= j->cutoff) ? s : 0.0f;
+            if (drop_zero && s == 0.0f)
+                continue;
+            j->survivors[q]++;
+            cand_t c = {s, (uint32_t) grow};
+            heap_push(&j->heaps[q], c);
+        }
+    }
+    free(popq);
+    free(commons);
+    return NULL;
+}
+
+void oracle_stream_search_multi(const int32_t* queries, int nq, int words, uint64_t seed,
+                                uint32_t plant_period, uint64_t n_rows, uint64_t row_base, uint32_t k,
+                                float cutoff, uint32_t* out_rows, float* out_scores, uint32_t* out_n,
+                                uint64_t* out_approx, int n_threads)
+{
+    if (n_threads < 1)
+        n_threads = 1;
+    mstream_job_t* jobs = (mstream_job_t*) calloc(n_threads, sizeof(mstream_job_t));
+    pthread_t* th = (pthread_t*) calloc(n_threads, sizeof(pthread_t));
+    const uint64_t per = (n_rows + n_threads - 1) / n_threads;
+    for (int t = 0; t < n_threads; t++) {
+        mstream_job_t* j = &jobs[t];
+        j->qs = queries; j->nq = nq; j->seed = seed; j->row_base = row_base; j->words = words;
+        j->plant_period = plant_period; j->cutoff = cutoff;
+        j->lo = (uint64_t) t * per < n_rows ? (uint64_t) t * per : n_rows;
+        j->hi = j->lo + per < n_rows ? j->lo + per : n_rows;
+        j->heaps = (heap_t*) calloc(nq, sizeof(heap_t));
+        j->survivors = (uint64_t*) calloc(nq, sizeof(uint64_t));
+        for (int q = 0; q < nq; q++) {
+            j->heaps[q].cap = k;
+            j->heaps[q].h = k ? (cand_t*) malloc((size_t) k * sizeof(cand_t)) : NULL;
+        }
+        pthread_create(&th[t], NULL, mstream_job, j);
+    }
+    for (int t = 0; t < n_threads; t++)
+        pthread_join(th[t], NULL);
+    cand_t* all = (cand_t*) malloc(((size_t) n_threads * k + 1) * sizeof(cand_t));
+    for (int q = 0; q < nq; q++) {
+        uint32_t total = 0;
+        uint64_t surv = 0;
+        for (int t = 0; t < n_threads; t++) {
+            memcpy(all + total, jobs[t].heaps[q].h, (size_t) jobs[t].heaps[q].n * sizeof(cand_t));
+            total += jobs[t].heaps[q].n;
+            surv += jobs[t].survivors[q];
+        }
+        qsort(all, total, sizeof(cand_t), cmp_canonical);
+        const uint32_t n = total < k ? total : k;
+        for (uint32_t i = 0; i < n; i++) {
+            out_rows[(size_t) q * k + i] = all[i].row;
+            out_scores[(size_t) q * k + i] = all[i].score;
+        }
+        out_n[q] = n;
+        out_approx[q] = cutoff > 0.0f ? surv : n_rows;
+    }
+    free(all);
+    for (int t = 0; t < n_threads; t++) {
+        for (int q = 0; q < nq; q++)
+            free(jobs[t].heaps[q].h);
+        free(jobs[t].heaps); free(jobs[t].survivors);
+    }
+    free(jobs); free(th);
+}

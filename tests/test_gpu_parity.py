@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 from conftest import f32bits
+from gpusimilarity_b200.dist import unpack_key
 from oracle import oracle as O
 from oracle import oracle_c as OC
 
@@ -35,6 +36,27 @@ def check(db, rows_np, query, k, cutoff, what=""):
     got = db.search_rows(query, k, cutoff)
     want = OC.c_search(query, rows_np, k, cutoff)
     assert_same(got, want, f"{what} k={k} cutoff={cutoff}")
+
+
+def assert_appendix_d(got, ref, query, rows_np, cutoff, what=""):
+    """SURVEY App. D parity rules against the reference's own CUDA path on a multi-chunk database,
+    where the reference's survivors of a tie group at the k boundary depend on heap addresses:
+    (i) score vectors equal as f32 bit patterns, (ii) the same rows above the k-th score,
+    (iii) every returned row at the k-th score really has that score; plus the approximate count."""
+    g_rows, g_scores, g_approx = got
+    r_rows, r_scores, r_approx = ref
+    assert g_approx == r_approx, f"{what}: approx {g_approx} != {r_approx}"
+    assert np.array_equal(f32bits(g_scores), f32bits(r_scores)), f"{what}: (i) score vectors differ"
+    if len(g_scores) == 0:
+        return
+    s_k = g_scores[-1]
+    assert sorted(g_rows[g_scores > s_k].tolist()) == sorted(r_rows[r_scores > s_k].tolist()), \
+        f"{what}: (ii) rows above the k-th score differ"
+    for rows, scores in ((g_rows, g_scores), (r_rows, r_scores)):
+        at = rows[scores == s_k]
+        assert len(set(at.tolist())) == len(at)
+        true = O.tanimoto_scores_gpu(query, rows_np[at], cutoff)
+        assert np.all(f32bits(true) == f32bits(np.float32(s_k))), f"{what}: (iii) boundary rows mis-scored"
 
 
 # ------------------------------------------------------------------ the reference's own tests
@@ -162,6 +184,122 @@ def test_other_widths(bits):
     assert np.array_equal(db.getFingerprint(77), rows_np[77])
 
 
+@pytest.mark.parametrize("metric,alpha,beta", [("dice", 1.0, 1.0), ("tversky", 1.0, 1.0), ("tversky", 0.5, 0.5),
+                                               ("tversky", 0.9, 0.1), ("tversky", 0.0, 1.0), ("tversky", 2.0, 0.3)])
+def test_dice_and_tversky(metric, alpha, beta):
+    """the other metrics share the scan, only the epilogue differs.  Single-query kernel,
+    multi-query kernel (the POPC one: the bit-sliced filter is Tanimoto's), folded re-score and
+    search_cpu against the oracle's definition; Tversky(1,1) must equal Tanimoto score for score."""
+    rows_np = O.synth_db(404, 90_000, 32, 37)
+    rows_np[100:140] = 0
+    db = make_db(rows_np)
+    db.setMetric(metric, alpha, beta)
+    qs = [O.synth_template(404, 32), rows_np[7], np.zeros(32, np.int32), np.full(32, -1, np.int32)]
+    for q in qs:
+        for k, cutoff in ((10, 0.0), (1000, 0.0), (200, 0.25), (50, 0.7)):
+            assert_same(db.search_rows(q, k, cutoff), O.search_gpu_metric(q, rows_np, k, cutoff, metric, alpha, beta),
+                        f"{metric}({alpha},{beta}) k={k} cutoff={cutoff}")
+    if metric == "tversky" and alpha == beta == 1.0:
+        assert_same(db.search_rows(qs[0], 500, 0.1), OC.c_search(qs[0], rows_np, 500, 0.1), "tversky(1,1) == tanimoto")
+    mode, per = db.batch_mode(100, len(qs))
+    for got, q in zip(db.search_batch_rows(np.stack(qs), 100, 0.05), qs):
+        assert_same(got, O.search_gpu_metric(q, rows_np, 100, 0.05, metric, alpha, beta), f"{metric} batch (mode {mode})")
+    many = np.stack([rows_np[i * 31] for i in range(40)])          # 40 queries would pick the bit-sliced kernel
+    assert db.batch_mode(100, 40)[0] == 1                           # ... but not for another metric: POPC kernel
+    for got, q in zip(db.search_batch_rows(many, 100, 0.0), many):
+        assert_same(got, O.search_gpu_metric(q, rows_np, 100, 0.0, metric, alpha, beta), f"{metric} 40-query batch")
+    db.setMetric("tanimoto")
+    check(db, rows_np, qs[0], 100, 0.0, "back to tanimoto")
+
+
+def test_async_tickets_keep_four_queries_in_flight():
+    """gsb_db_search_async / _wait: four tickets outstanding, waited out of order; the fifth is refused
+    until one is waited for; folded databases and very large k answer through the same two calls."""
+    rows_np = O.synth_db(515, 250_000, 32, 29)
+    db = make_db(rows_np)
+    qs = [O.synth_template(515, 32), rows_np[1], rows_np[249_999], np.zeros(32, np.int32), rows_np[77]]
+    want = [OC.c_search(q, rows_np, 1000, 0.1) for q in qs]
+    for rep in range(3):
+        tickets = [db.search_rows_async(q, 1000, 0.1) for q in qs[:4]]
+        with pytest.raises(gsb.GsbError):
+            db.search_rows_async(qs[4], 1000, 0.1)
+        assert_same(db.search_rows(qs[4], 1000, 0.1), want[4], "sync call between async ones")
+        for i in (2, 0, 3, 1):
+            assert_same(db.search_rows_wait(tickets[i]), want[i], f"rep {rep} ticket {i}")
+    # pipelined: always two in flight
+    t_prev = db.search_rows_async(qs[0], 1000, 0.1)
+    for i in range(1, 40):
+        t = db.search_rows_async(qs[i % 5], 1000, 0.1)
+        assert_same(db.search_rows_wait(t_prev), want[(i - 1) % 5], f"pipelined {i}")
+        t_prev = t
+    assert_same(db.search_rows_wait(t_prev), want[39 % 5], "pipelined tail")
+    t = db.search_rows_async(qs[0], 30_000, 0.0)                    # more than one launch can select
+    assert_same(db.search_rows_wait(t), OC.c_search(qs[0], rows_np, 30_000, 0.0), "deferred large k")
+    folded = make_db(rows_np, fold=4)
+    t = folded.search_rows_async(qs[0], 20, 0.3)
+    r, s_, a = folded.search_rows_wait(t)
+    w = O.search_gpu_folded(qs[0], rows_np, 20, 0.3, 4)
+    assert a == w[2] and np.array_equal(r, w[0]) and np.array_equal(f32bits(s_), f32bits(w[1]))
+
+
+def test_searches_on_different_streams_are_ordered():
+    """two device searches of one database on different streams share the shard's
+    workspace; the library orders them itself (event on the earlier stream's tail)."""
+    import torch
+    from gpusimilarity_b200.dist import ShardedSearcher
+    n, k, seed = 3_000_000, 1000, 626
+    rows_np = OC.c_synth_db(seed, n, 32, 900)
+    db = make_db(rows_np)
+    dev = torch.device("cuda", 0)
+    qs = [O.synth_template(seed, 32), rows_np[5], rows_np[n - 1]]
+    d_qs = [torch.from_numpy(np.ascontiguousarray(q)).to(dev) for q in qs]
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    searchers = [ShardedSearcher(db, k, 0) for _ in range(3)]
+    torch.cuda.synchronize()
+    for rep in range(5):
+        for i in range(3):                         # three launches back to back on three streams
+            searchers[i].search_local(d_qs[i].data_ptr(), 0.0, streams[i])
+        got_sync = db.search_rows(qs[rep % 3], k, 0.0)   # and the host-buffer call on the library's own stream
+        torch.cuda.synchronize()
+        for i in range(3):
+            rec = searchers[i].rec.cpu().numpy().view(np.uint64)
+            cnt = int(rec[k + 1]) & 0xffffffff
+            rows, scores = unpack_key(rec[:cnt])
+            assert_same((rows, scores, int(rec[k])), OC.c_search(qs[i], rows_np, k, 0.0), f"stream {i} rep {rep}")
+        assert_same(got_sync, OC.c_search(qs[rep % 3], rows_np, k, 0.0), "host-buffer call in between")
+
+
+def test_peer_flag_timeout_is_an_error_not_a_dead_context(monkeypatch):
+    """Fault injection: a fused search whose peer never shows up must end in an error
+    value — GSB_COUNT_ERROR in *n, raised by wait_host — and leave the context and the database usable."""
+    import ctypes as C
+    import torch
+    from gpusimilarity_b200._lib import Exchange, Sink, check, lib
+    monkeypatch.setenv("GSB_SPIN_TIMEOUT_MS", "200")
+    n, k = 200_000, 100
+    rows_np = O.synth_db(909, n, 32, 0)
+    shard = gsb.FingerprintDB.synthetic(n, device=0, seed=909)
+    dev = torch.device("cuda", 0)
+    nbytes = C.c_uint64(0)
+    check(lib().gsb_exchange_bytes(2, k, C.byref(nbytes)))
+    mine, peer = (torch.zeros(nbytes.value, dtype=torch.uint8, device=dev) for _ in range(2))
+    x = Exchange()
+    x.peer_base[0], x.peer_base[1] = mine.data_ptr(), peer.data_ptr()
+    x.rank, x.world, x.seq = 0, 2, 1
+    out_rows = torch.zeros(k, dtype=torch.int32, device=dev)
+    out_scores = torch.zeros(k, dtype=torch.float32, device=dev)
+    out_n = torch.zeros(1, dtype=torch.int32, device=dev)
+    out_approx = torch.zeros(1, dtype=torch.int64, device=dev)
+    q = O.synth_template(909, 32)
+    sink = Sink(rows=out_rows.data_ptr(), scores=out_scores.data_ptr(), n=out_n.data_ptr(), approx=out_approx.data_ptr())
+    check(lib().gsb_db_search_enqueue(shard._h, torch.cuda.current_stream().cuda_stream, q.ctypes.data, None, 0, k, 0.0,
+                                      C.byref(x), C.byref(sink)))
+    torch.cuda.synchronize()                                   # returns: the kernel gave up after 200 ms
+    assert (int(out_n.item()) & 0xffffffff) == 0xffffffff      # GSB_COUNT_ERROR
+    # the context is alive and the same shard answers the next query correctly
+    assert_same(shard.search_rows(q, k, 0.0), OC.c_search(q, rows_np, k, 0.0), "after the injected fault")
+
+
 def test_rowpop_layout_variant(monkeypatch):
     monkeypatch.setenv("GSB_ROWPOP", "0")
     rows_np = O.synth_db(555, 70001, 32, 19)
@@ -263,6 +401,71 @@ def test_against_reference_cuda_path():
             assert np.array_equal(f32bits(scores), f32bits(r_scores))
             order = O.canonical_order(r_scores, r_rows)
             assert np.array_equal(rows, r_rows[order])
+
+
+@pytest.mark.skipif(not OC.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("fold", [2, 4, 8])
+def test_folded_search_against_reference_cuda_path(fold):
+    """reference copyToGPU(F) + search (fingerprintdb_cuda.cu:168-195, 246-331) running live on this
+    GPU against gsb_db_search on the same rows, and the numpy restatement against both.  One chunk:
+    the result SET and the score vector must match; the reference orders equal scores by pointer."""
+    n = 400_000
+    rows_np = OC.c_synth_db(6100 + fold, n, 32, 250)
+    ref = OC.RefDB([rows_np], 1024)
+    ref.copy_to_gpu(fold)
+    db = make_db(rows_np, fold=fold)
+    for q in (O.synth_template(6100 + fold, 32), rows_np[4242]):
+        for k, cutoff in ((10, 0.0), (100, 0.0), (20, 0.3), (100, 0.55), (1000, 0.2)):
+            r_rows, r_scores, r_approx = ref.search(q, k, cutoff)
+            rows, scores, approx = db.search_rows(q, k, cutoff)
+            what = f"fold {fold} k {k} cutoff {cutoff}"
+            assert approx == r_approx, what
+            assert np.array_equal(f32bits(scores), f32bits(r_scores)), what
+            assert np.array_equal(rows[O.canonical_order(scores, rows)], r_rows[O.canonical_order(r_scores, r_rows)]), what
+            w_rows, w_scores, w_approx = O.search_gpu_folded(q, rows_np, k, cutoff, fold)
+            assert w_approx == r_approx and np.array_equal(f32bits(w_scores), f32bits(r_scores)), what
+            assert sorted(w_rows.tolist()) == sorted(r_rows.tolist()), what
+
+
+@pytest.mark.skipif(not OC.ref_available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("n", [10_000_000, 20_000_000])
+def test_multi_chunk_against_reference_cuda_path(n):
+    """BASELINE configs[1] the way gpusimserver holds it: chunks of 2^23 rows (1 GiB, what
+    gpusim_createdb writes), searched by the reference's own CUDA path and by this engine from the
+    same chunk list.  Checked with the cross-chunk rules of SURVEY App. D (i)-(iii); a tie group
+    planted across two chunk boundaries makes the k-th score a tie on purpose."""
+    chunk = 1 << 23
+    rows_np = OC.c_synth_db(n, n, 32, 4096)
+    q = O.synth_template(n, 32)
+    dup = rows_np[777].copy()                        # 60 identical rows straddling both chunk boundaries
+    for b in range(1, (n + chunk - 1) // chunk):
+        rows_np[b * chunk - 30:b * chunk + 30] = dup
+    chunks = [rows_np[a:a + chunk] for a in range(0, n, chunk)]
+    ref = OC.RefDB(chunks, 1024)
+    ref.copy_to_gpu(1)
+    db = gsb.FingerprintDB(1024, n, "pass", chunks)
+    db.copyToGPU(1)
+    for query, cases in ((q, ((1000, 0.0), (1000, 0.3), (10, 0.0))), (dup, ((40, 0.0), (1000, 0.0), (25, 0.9)))):
+        for k, cutoff in cases:
+            got = db.search_rows(query, k, cutoff)
+            assert_appendix_d(got, ref.search(query, k, cutoff), query, rows_np, cutoff, f"n={n} k={k} cutoff={cutoff}")
+            assert_same(got, OC.c_search(query, rows_np, k, cutoff), f"oracle n={n} k={k} cutoff={cutoff}")
+    for r in (0, chunk - 1, chunk, chunk + 1, n - 1):   # row lookup across chunk boundaries (a8)
+        assert np.array_equal(db.getFingerprint(r), rows_np[r])
+
+
+@pytest.mark.parametrize("n", [200_000_000, 1_000_000_000])
+def test_full_size_against_streamed_oracle(n):
+    """BASELINE configs[2] (1 B x 1024 bit, one query, top-1000) bit for bit: the oracle streams the
+    same synthetic rows through its scorer on the host cores (generated on the fly, never stored) and
+    must return the same rows, f32 score bits and approximate counts as the one-launch GPU search."""
+    seed, plant, k = 77, 50000, 1000
+    q = O.synth_template(seed, 32)
+    whole = gsb.FingerprintDB.synthetic(n, device=0, seed=seed, plant_period=plant)
+    for query, cutoff in ((q, 0.0), (q, 0.08), (whole.getFingerprint(n - 7), 0.0)):
+        got = whole.search_rows(query, k, cutoff)
+        assert_same(got, OC.c_stream_search(query, seed, plant, n, k, cutoff), f"streamed oracle n={n} cutoff={cutoff}")
+    whole.close()
 
 
 @pytest.mark.parametrize("n", [200_000_000, 1_000_000_000])
@@ -614,25 +817,39 @@ def test_fused_peer_exchange_two_ranks_on_one_gpu(monkeypatch):
             assert_same(got, want, f"fused rank {r} seq {seq}")
 
 
-@pytest.mark.skipif(gsb.get_gpu_count() < 2, reason="needs two GPUs in one process")
-def test_single_process_multi_device_shards():
+def _shard_device_lists():
+    lists = [[0, 0, 0], [0, 0, 0, 0, 0]]     # several shards on ONE device: what a 1-GPU box can run
+    if gsb.get_gpu_count() >= 2:
+        lists.append(list(range(min(gsb.get_gpu_count(), 4))))
+    return lists
+
+
+@pytest.mark.parametrize("devices", _shard_device_lists(), ids=lambda d: "dev" + "".join(map(str, d)))
+def test_single_process_multi_device_shards(devices):
     """The reference's own multi-GPU mode: one process, chunks spread over the visible devices
-    (fingerprintdb_cuda.cu:176-183), per-device results merged on the host (:366)."""
+    (fingerprintdb_cuda.cu:176-183), per-device results merged (:366).  A device may be listed more
+    than once: every entry is a shard with its own row range, stream and workspace, so the sharding,
+    the per-shard launches and the merge are exercised on a one-GPU box too."""
     n = 2_000_001
     rows_np = OC.c_synth_db(71, n, 32, 900)
-    devices = list(range(min(gsb.get_gpu_count(), 4)))
+    rows_np[n // 3 - 20:n // 3 + 20] = rows_np[5]          # a tie group across a shard boundary
     db = make_db(rows_np, devices=devices)
     assert db.shardCount() == len(devices)
     qs = [O.synth_template(71, 32), rows_np[0], rows_np[n - 1]]
+    qs.append(rows_np[5])
     for q in qs:
-        for k, cutoff in ((10, 0.0), (1000, 0.0), (1000, 0.2), (20000, 0.0)):
+        for k, cutoff in ((10, 0.0), (30, 0.0), (1000, 0.0), (1000, 0.2), (20000, 0.0)):
             check(db, rows_np, q, k, cutoff, f"{len(devices)} devices")
+    for r in (0, n // 3, n - 1):
+        assert np.array_equal(db.getFingerprint(r), rows_np[r])
     res = db.search_batch_rows(np.stack(qs), 100, 0.1)
     for q, got in zip(qs, res):
         assert_same(got, OC.c_search(q, rows_np, 100, 0.1), "multi-device batch")
     db2 = make_db(rows_np, fold=2, devices=devices)
     rows, scores, approx = db2.search_rows(qs[0], 10, 0.3)
-    assert np.all(scores >= np.float32(0.3)) and np.all(np.diff(scores) <= 0)
+    w_rows, w_scores, w_approx = O.search_gpu_folded(qs[0], rows_np, 10, 0.3, 2)
+    assert approx == w_approx and np.array_equal(f32bits(scores), f32bits(w_scores))
+    assert sorted(rows.tolist()) == sorted(w_rows.tolist())
 
 
 def test_multi_chunk_upload():
