@@ -20,11 +20,12 @@ $(SERVER): $(CSRC)/gpusimserver_main.cpp $(LIB)
 # in this image, so this target compile-checks and tests it against the header-only Qt stand-ins
 # in oracle/qt_shims; with real Qt, build it with -I<Qt include dirs> instead.
 ADAPTER := gpusimilarity_b200/libgpusim_adapter.so
-$(ADAPTER): $(CSRC)/fingerprintdb_adapter.cpp include/gpusim/fingerprintdb_cuda.h include/gpusim/calculation_functors.h $(LIB)
+$(ADAPTER): $(CSRC)/fingerprintdb_adapter.cpp include/gpusim/fingerprintdb_cuda.h include/gpusim/calculation_functors.h \
+            oracle/qt_shims/gsb_qt_shim_core.h $(LIB)
 	g++ -std=c++14 -O2 -fPIC -Wall -Werror -shared -Iinclude -Ioracle/qt_shims -o $@ $(CSRC)/fingerprintdb_adapter.cpp \
 	    -Lgpusimilarity_b200 -lgpusim_b200 -Wl,-rpath,'$$ORIGIN'
 
-tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER)
+tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER) oracle/qt_shims/gsb_qt_shim_core.h
 	g++ -std=c++14 -O2 -Wall -Iinclude -Ioracle/qt_shims -o $@ tests/cpp/test_adapter.cpp \
 	    -Lgpusimilarity_b200 -lgpusim_adapter -lgpusim_b200 -Wl,-rpath,'$$ORIGIN/../../gpusimilarity_b200'
 

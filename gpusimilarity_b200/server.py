@@ -146,3 +146,15 @@ def search_over_socket(request: bytes, socket_path: str = SOCKET_PATH, timeout: 
                 except (struct.error, IndexError):
                     continue
         return buf
+
+
+def search_socket(socket_path: str, dbname_to_key: Dict[str, str], fingerprint: Sequence[int], results_requested: int,
+                  similarity_cutoff: float, request_num: int = 1, timeout: float = 30.0):
+    """One search against a running daemon (this repo's or the reference's): returns
+    (approximate_count, smiles, ids, scores) with the strings decoded."""
+    buf = search_over_socket(encode_request(dbname_to_key, request_num, results_requested, similarity_cutoff,
+                                            fingerprint), socket_path, timeout)
+    got_num, approx, smiles, ids, scores = decode_response(buf)
+    if got_num != request_num:
+        raise GsbError(6, f"response for request {got_num}, expected {request_num}")
+    return approx, [x.decode() for x in smiles], [x.decode() for x in ids], scores

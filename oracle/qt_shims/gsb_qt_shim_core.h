@@ -25,6 +25,10 @@
 #include <thrust/remove.h>
 #endif
 
+#define QT_VERSION_CHECK(major, minor, patch) ((major << 16) | (minor << 8) | (patch))
+#define QT_VERSION QT_VERSION_CHECK(5, 15, 0)
+typedef unsigned long long quint64;
+
 class QString
 {
   public:
@@ -35,15 +39,100 @@ class QString
     bool operator!=(const QString& o) const { return m_s != o.m_s; }
     bool operator<(const QString& o) const { return m_s < o.m_s; }
     const std::string& toStdString() const { return m_s; }
+    bool isEmpty() const { return m_s.empty(); }
+    // "%1".arg(x): replaces the lowest-numbered place marker
+    QString arg(const QString& a) const
+    {
+        for (int n = 1; n < 10; n++) {
+            const std::string marker = "%" + std::to_string(n);
+            const size_t pos = m_s.find(marker);
+            if (pos != std::string::npos) {
+                std::string out = m_s;
+                out.replace(pos, marker.size(), a.m_s);
+                return QString(out);
+            }
+        }
+        return *this;
+    }
+    int toInt(bool* ok = nullptr) const
+    {
+        char* end = nullptr;
+        const long v = std::strtol(m_s.c_str(), &end, 10);
+        const bool good = !m_s.empty() && end && *end == '\0';
+        if (ok)
+            *ok = good;
+        return good ? static_cast<int>(v) : 0;
+    }
 
   private:
     std::string m_s;
 };
+#define qPrintable(s) ((s).toStdString().c_str())
+inline unsigned int qHash(const QString& s) { return static_cast<unsigned int>(std::hash<std::string>()(s.toStdString())); }
+namespace std
+{
+template <> struct hash<QString> {
+    std::size_t operator()(const QString& s) const { return std::hash<std::string>()(s.toStdString()); }
+};
+} // namespace std
 
+class QStringList : public std::vector<QString>
+{
+  public:
+    QStringList& operator<<(const QString& s)
+    {
+        push_back(s);
+        return *this;
+    }
+};
+
+// Parent / child ownership, sender() and pointer-to-member connect(): what the reference's
+// GPUSimServer uses of QObject (gpusim.cpp:255-274, 294-304).  Signals are ordinary member
+// functions of the stand-in classes; a class with signals implements gsbConnect().
+#define slots
+#define signals public
 class QObject
 {
   public:
-    virtual ~QObject() = default;
+    explicit QObject(QObject* parent = nullptr) : m_parent(parent)
+    {
+        if (parent)
+            parent->m_children.push_back(this);
+    }
+    virtual ~QObject()
+    {
+        if (m_parent) {
+            auto& c = m_parent->m_children;
+            c.erase(std::remove(c.begin(), c.end(), this), c.end());
+        }
+        std::vector<QObject*> kids;
+        kids.swap(m_children);
+        for (QObject* k : kids) {
+            k->m_parent = nullptr;
+            delete k;
+        }
+    }
+    QObject(const QObject&) = delete;
+    QObject& operator=(const QObject&) = delete;
+    QObject* sender() const { return m_sender; }
+    void gsbSetSender(QObject* s) { m_sender = s; }
+    void deleteLater() { m_delete_later = true; }
+    bool gsbDeleteRequested() const { return m_delete_later; }
+    template <class Snd, class Sig, class Rcv, class Slt>
+    static bool connect(Snd* sender, Sig signal, Rcv* receiver, Slt slot)
+    {
+        return sender->gsbConnect(signal, [sender, receiver, slot]() {
+            receiver->gsbSetSender(sender);
+            (receiver->*slot)();
+            receiver->gsbSetSender(nullptr);
+        });
+    }
+
+  private:
+    QObject* m_parent = nullptr;
+    QObject* m_sender = nullptr;
+    bool m_delete_later = false;
+    std::vector<QObject*> m_children;
 };
 
 // qDebug()/qInfo(): swallow the stream unless GSB_REF_VERBOSE is set.
@@ -76,6 +165,7 @@ class GsbShimDebug
 };
 inline GsbShimDebug qDebug() { return GsbShimDebug(); }
 inline GsbShimDebug qInfo() { return GsbShimDebug(); }
+inline GsbShimDebug qWarning() { return GsbShimDebug(); }
 
 class QMutex
 {
@@ -98,8 +188,38 @@ template <typename T> class QFuture
     std::shared_future<T> m_f;
 };
 
+// QRunnable / QThreadPool as GPUSimServer::extractData uses them (gpusim.cpp:48-85, 202-236):
+// start() runs the job on its own thread and deletes it (autoDelete), waitForDone() joins.
+class QRunnable
+{
+  public:
+    virtual ~QRunnable() = default;
+    virtual void run() = 0;
+};
 class QThreadPool
 {
+  public:
+    ~QThreadPool() { waitForDone(); }
+    void start(QRunnable* job)
+    {
+        // never more jobs in flight than cores (Qt: maxThreadCount = ideal thread count)
+        unsigned n = std::thread::hardware_concurrency();
+        if (m_threads.size() >= (n ? n : 1u))
+            waitForDone();
+        m_threads.emplace_back([job]() {
+            job->run();
+            delete job;
+        });
+    }
+    void waitForDone()
+    {
+        for (auto& t : m_threads)
+            t.join();
+        m_threads.clear();
+    }
+
+  private:
+    std::vector<std::thread> m_threads;
 };
 
 namespace QtConcurrent
