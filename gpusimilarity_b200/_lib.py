@@ -50,6 +50,8 @@ SIGNATURES = {
     "gsb_device_free_bytes": (C.c_uint64, [C.c_int]),
     "gsb_available_device_bytes": (C.c_uint64, []),
     "gsb_next_device": (C.c_int, [C.c_uint64, C.POINTER(C.c_int)]),
+    "gsb_devices_reset": (C.c_int, []),
+    "gsb_layout_bytes": (C.c_uint64, [C.c_int, C.c_uint64, C.c_uint]),
     "gsb_db_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint64,
                                 C.POINTER(_P)]),
     "gsb_db_create_synthetic": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
@@ -96,6 +98,7 @@ SIGNATURES = {
     "gsb_fsim_create_db": (C.c_int, [_P, C.POINTER(_P)]),
     "gsb_server_create": (C.c_int, [C.POINTER(C.c_char_p), C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "gsb_server_destroy": (None, [_P]),
+    "gsb_server_recover": (C.c_int, [_P]),
     "gsb_server_last_error": (C.c_char_p, []),
     "gsb_server_set_use_gpu": (None, [_P, C.c_int]),
     "gsb_server_using_gpu": (C.c_int, [_P]),

@@ -92,6 +92,10 @@ void split_strings(const std::vector<uint8_t>& raw, std::vector<const char*>* ou
             *err = "truncated string block";
             return;
         }
+        if (n && p[n - 1] != 0) { // every entry is handed out as a C string: it must end inside its bytes
+            *err = "string entry without terminating NUL";
+            return;
+        }
         out->push_back(n ? reinterpret_cast<const char*>(p) : "");
     }
 }
@@ -111,6 +115,7 @@ const char* gsb_fsim_last_error(void) { return g_fsim_err.c_str(); }
 
 int gsb_fsim_open(const char* path, gsb_fsim** out)
 {
+    try {
     if (!path || !out) {
         g_fsim_err = "null argument";
         return GSB_ERR_INVALID;
@@ -183,8 +188,22 @@ int gsb_fsim_open(const char* path, gsb_fsim** out)
         g_fsim_err = err;
         return GSB_ERR_IO;
     }
+    // a row without its SMILES / id would crash the server at query time: fail at load instead
+    if (f->smiles_ptrs.size() != f->fp_count || f->id_ptrs.size() != f->fp_count) {
+        g_fsim_err = "SMILES / id counts (" + std::to_string(f->smiles_ptrs.size()) + " / " +
+                     std::to_string(f->id_ptrs.size()) + ") do not match the fingerprint count " +
+                     std::to_string(f->fp_count) + ", potential database corruption.";
+        return GSB_ERR_CORRUPT;
+    }
     *out = f.release();
     return GSB_OK;
+    } catch (const std::bad_alloc&) {
+        g_fsim_err = "out of host memory";
+        return GSB_ERR_NOMEM;
+    } catch (const std::exception& e) {
+        g_fsim_err = std::string("exception: ") + e.what();
+        return GSB_ERR_IO;
+    }
 }
 
 void gsb_fsim_close(gsb_fsim* f) { delete f; }

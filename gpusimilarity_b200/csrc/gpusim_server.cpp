@@ -31,6 +31,7 @@
 namespace
 {
 thread_local std::string g_srv_err;
+thread_local int g_last_rc = GSB_OK; // code of the latest failed search (the serve loop recovers from GSB_ERR_CUDA)
 
 struct Database {
     std::string name, key;
@@ -153,6 +154,8 @@ struct gsb_server {
         *approx = 0;
         if (key != d.key) // fingerprintdb_cuda.cu:349-352: silently empty
             return GSB_OK;
+        // the request's result count comes straight from the socket: never size buffers by it alone
+        k = static_cast<unsigned>(std::min<uint64_t>(k, gsb_db_count(d.db)));
         std::vector<uint32_t> rows(k ? k : 1);
         std::vector<float> scores(rows.size());
         uint32_t n = 0;
@@ -163,10 +166,14 @@ struct gsb_server {
             rc = gsb_db_search_cpu(d.db, q, n_words, k, rows.data(), scores.data(), &n);
         if (rc != GSB_OK) {
             g_srv_err = gsb_last_error();
+            g_last_rc = rc;
             return rc;
         }
-        for (uint32_t i = 0; i < n; i++)
-            out->push_back({scores[i], gsb_fsim_string(d.file, 0, rows[i]), gsb_fsim_string(d.file, 1, rows[i])});
+        for (uint32_t i = 0; i < n; i++) {
+            const char* smi = gsb_fsim_string(d.file, 0, rows[i]);
+            const char* id = gsb_fsim_string(d.file, 1, rows[i]);
+            out->push_back({scores[i], smi ? smi : "", id ? id : ""});
+        }
         return GSB_OK;
     }
 
@@ -236,6 +243,8 @@ struct gsb_server {
     {
         Reader rd{data, len};
         const int n_db = rd.i32();
+        if (n_db < 0 || n_db > 4096) // every entry takes at least 8 bytes of the request
+            return false;
         for (int i = 0; i < n_db && rd.ok; i++) {
             std::string name = rd.cstr();
             std::string key = rd.cstr();
@@ -297,7 +306,7 @@ struct gsb_server {
         const Request& first = *group[0];
         const size_t nq = group.size();
         const int n_words = static_cast<int>(first.query.size());
-        const unsigned k = static_cast<unsigned>(std::max(first.results_requested, 0));
+        const unsigned k_req = static_cast<unsigned>(std::max(first.results_requested, 0));
         std::map<std::string, std::string> ordered(first.name_key.begin(), first.name_key.end());
         std::vector<std::vector<Result>> all(nq);
         std::vector<uint64_t> approx_total(nq, 0);
@@ -309,6 +318,7 @@ struct gsb_server {
             if (it == dbs.end() || nk.second != it->second->key)
                 continue;
             Database& d = *it->second;
+            const unsigned k = static_cast<unsigned>(std::min<uint64_t>(k_req, gsb_db_count(d.db)));
             std::vector<uint32_t> rows(nq * std::max(k, 1u)), cnt(nq);
             std::vector<float> scores(rows.size());
             std::vector<uint64_t> approx(nq);
@@ -316,13 +326,16 @@ struct gsb_server {
                                                rows.data(), scores.data(), cnt.data(), approx.data());
             if (rc != GSB_OK) {
                 g_srv_err = gsb_last_error();
+                g_last_rc = rc;
                 return rc;
             }
             for (size_t q = 0; q < nq; q++) {
                 approx_total[q] += approx[q];
-                for (uint32_t i = 0; i < cnt[q]; i++)
-                    all[q].push_back({scores[q * k + i], gsb_fsim_string(d.file, 0, rows[q * k + i]),
-                                      gsb_fsim_string(d.file, 1, rows[q * k + i])});
+                for (uint32_t i = 0; i < cnt[q]; i++) {
+                    const char* smi = gsb_fsim_string(d.file, 0, rows[q * k + i]);
+                    const char* id = gsb_fsim_string(d.file, 1, rows[q * k + i]);
+                    all[q].push_back({scores[q * k + i], smi ? smi : "", id ? id : ""});
+                }
             }
         }
         responses->resize(nq);
@@ -336,12 +349,60 @@ struct gsb_server {
     }
 };
 
+// No exception may cross the C ABI (a request asking for 2^31 results must not end in
+// std::terminate inside the hosting process).
+#define SRV_TRY try {
+#define SRV_CATCH                                                                                \
+    }                                                                                            \
+    catch (const std::bad_alloc&)                                                                \
+    {                                                                                            \
+        g_srv_err = "out of host memory";                                                        \
+        return GSB_ERR_NOMEM;                                                                    \
+    }                                                                                            \
+    catch (const std::exception& e)                                                              \
+    {                                                                                            \
+        g_srv_err = std::string("exception: ") + e.what();                                       \
+        return GSB_ERR_INVALID;                                                                  \
+    }                                                                                            \
+    catch (...)                                                                                  \
+    {                                                                                            \
+        g_srv_err = "unknown exception";                                                         \
+        return GSB_ERR_INVALID;                                                                  \
+    }
+
 extern "C" {
 
 const char* gsb_server_last_error(void) { return g_srv_err.c_str(); }
 
+// Failure containment for the daemon: after a search came back with GSB_ERR_CUDA the databases are
+// put up again — first on the context as it is (the kernels report barrier / peer timeouts through
+// an error word and leave the context usable), and if that fails too after a reset of every
+// device.  The host rows and strings are untouched, so nothing has to be read from disk again.
+int gsb_server_recover(gsb_server* srv)
+{
+    SRV_TRY
+    if (!srv)
+        return GSB_ERR_INVALID;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (attempt == 1 && gsb_devices_reset() != GSB_OK)
+            break;
+        bool ok = true;
+        for (auto& kv : srv->dbs)
+            if (gsb_db_upload(kv.second->db, nullptr, 0, srv->fold_factor) != GSB_OK) {
+                g_srv_err = gsb_last_error();
+                ok = false;
+                break;
+            }
+        if (ok)
+            return GSB_OK;
+    }
+    return GSB_ERR_CUDA;
+    SRV_CATCH
+}
+
 int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcount, int use_gpu, gsb_server** out)
 {
+    SRV_TRY
     if (!out || n_paths < 0 || (n_paths > 0 && !fsim_paths)) {
         g_srv_err = "null argument";
         return GSB_ERR_INVALID;
@@ -378,6 +439,19 @@ int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcou
         if (total_db_memory > gpu_memory && gpu_memory > 0)
             fold_factor = static_cast<unsigned>(std::ceil(static_cast<float>(total_db_memory) /
                                                           static_cast<float>(gpu_memory)));
+        // The reference sizes against raw bytes; what has to fit is the device layout (rows padded to
+        // a power-of-two width, 2 B popcount per row) plus the upload staging and the multi-query
+        // workspaces: fold further until that fits, instead of failing the upload with NOMEM.
+        const uint64_t headroom = (3ull << 30) * static_cast<uint64_t>(gsb_device_count());
+        auto footprint = [&srv](unsigned f) {
+            uint64_t sum = 0;
+            for (auto& kv : srv->dbs)
+                sum += gsb_layout_bytes(gsb_db_fp_bits(kv.second->db), gsb_db_count(kv.second->db), f);
+            return sum;
+        };
+        while (gpu_memory > headroom && footprint(fold_factor) > gpu_memory - headroom &&
+               fold_factor < static_cast<unsigned>(max_bitcount / 32))
+            fold_factor++;
     }
     if (gpu_bitcount > 0) {
         const unsigned arg_fold_factor = static_cast<unsigned>(max_bitcount / gpu_bitcount);
@@ -399,6 +473,7 @@ int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcou
     }
     *out = srv.release();
     return GSB_OK;
+    SRV_CATCH
 }
 
 void gsb_server_destroy(gsb_server* srv)
@@ -436,6 +511,7 @@ int gsb_server_get_fingerprint(const gsb_server* srv, const char* dbname, uint64
 int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t request_bytes, void** response,
                               uint64_t* response_bytes)
 {
+    SRV_TRY
     std::vector<uint8_t> out;
     const int rc = srv->handle_request(static_cast<const uint8_t*>(request), request_bytes, &out);
     if (rc != GSB_OK)
@@ -444,6 +520,7 @@ int gsb_server_handle_request(gsb_server* srv, const void* request, uint64_t req
     std::memcpy(*response, out.data(), out.size());
     *response_bytes = out.size();
     return GSB_OK;
+    SRV_CATCH
 }
 
 void gsb_server_free(void* p) { std::free(p); }
@@ -453,6 +530,7 @@ void gsb_server_free(void* p) { std::free(p); }
 int gsb_server_handle_batch(gsb_server* srv, const void* const* requests, const uint64_t* request_bytes, int n,
                             void** responses, uint64_t* response_bytes)
 {
+    SRV_TRY
     if (n <= 0 || !requests || !request_bytes || !responses || !response_bytes) {
         g_srv_err = "null argument";
         return GSB_ERR_INVALID;
@@ -486,6 +564,7 @@ int gsb_server_handle_batch(gsb_server* srv, const void* const* requests, const 
         response_bytes[i] = out[i].size();
     }
     return GSB_OK;
+    SRV_CATCH
 }
 
 // GPUSimServer::setupSocket (gpusim.cpp:255-274): listen on <dir>/<name> ("/tmp/gpusimilarity"),
@@ -517,6 +596,7 @@ void gsb_server_stop(gsb_server* srv) { srv->stop = true; }
 // after gsb_server_stop() or after max_requests (0 = unlimited) were answered.
 int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
 {
+    SRV_TRY
     if (srv->listen_fd < 0) {
         g_srv_err = "not listening";
         return GSB_ERR_STATE;
@@ -524,14 +604,24 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
     std::vector<pollfd> fds{{srv->listen_fd, POLLIN, 0}};
     std::map<int, std::vector<uint8_t>> pending;
     uint64_t served = 0;
+    // MSG_NOSIGNAL: a client that went away while its search ran must not kill the daemon (and the
+    // databases it holds) with SIGPIPE; the connection is dropped when its read side reports EOF
     auto send_all = [](int fd, const std::vector<uint8_t>& buf) {
         size_t sent = 0;
         while (sent < buf.size()) {
-            const ssize_t w = write(fd, buf.data() + sent, buf.size() - sent);
+            const ssize_t w = send(fd, buf.data() + sent, buf.size() - sent, MSG_NOSIGNAL);
             if (w <= 0)
                 break;
             sent += static_cast<size_t>(w);
         }
+    };
+    // a failed search still gets a well-formed (empty) response, so that the client does not sit
+    // out its 30 s timeout; the reason goes to stderr
+    auto send_empty = [&send_all](int fd, const gsb_server::Request& r, const char* why) {
+        std::fprintf(stderr, "[gpusimserver] request %d failed: %s\n", r.request_num, why);
+        std::vector<uint8_t> response;
+        gsb_server::write_response(r, {}, {}, {}, 0, &response);
+        send_all(fd, response);
     };
     while (!srv->stop && (max_requests == 0 || served < max_requests)) {
         if (poll(fds.data(), fds.size(), 100) <= 0)
@@ -587,6 +677,12 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
                 if (srv->handle_batch(group, &responses) == GSB_OK)
                     for (size_t g = 0; g < members.size(); g++)
                         send_all(ready[members[g]].first, responses[g]);
+                else {
+                    for (size_t m : members)
+                        send_empty(ready[m].first, ready[m].second, g_srv_err.c_str());
+                    if (g_last_rc == GSB_ERR_CUDA)
+                        gsb_server_recover(srv);
+                }
             } else {
                 for (size_t m : members) {
                     const auto& r = ready[m].second;
@@ -598,6 +694,10 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
                                               r.cutoff, r.name_key, &smiles, &ids, &scores, &approx) == GSB_OK) {
                         gsb_server::write_response(r, smiles, ids, scores, approx, &response);
                         send_all(ready[m].first, response);
+                    } else {
+                        send_empty(ready[m].first, r, g_srv_err.c_str());
+                        if (g_last_rc == GSB_ERR_CUDA)
+                            gsb_server_recover(srv);
                     }
                 }
             }
@@ -605,6 +705,7 @@ int gsb_server_serve(gsb_server* srv, uint64_t max_requests)
         }
     }
     return GSB_OK;
+    SRV_CATCH
 }
 
 } // extern "C"

@@ -1528,6 +1528,37 @@ uint64_t gsb_available_device_bytes(void)
     return sum;
 }
 
+uint64_t gsb_layout_bytes(int fp_bits, uint64_t rows, unsigned fold_factor)
+{
+    if (fp_bits <= 0 || fp_bits % 32 != 0)
+        return 0;
+    const uint32_t words = static_cast<uint32_t>(fp_bits / 32);
+    unsigned f = std::max(1u, fold_factor);
+    while (words % f != 0) // copyToGPU's normalisation, reference .cu:170-173
+        f++;
+    Layout l;
+    if (make_layout(words / f, &l) != GSB_OK)
+        return 0;
+    const uint64_t tiles = (rows + l.tile_rows - 1) / l.tile_rows;
+    return tiles * l.tile_stride + l.unit_bytes;
+}
+
+int gsb_devices_reset(void)
+{
+    const int n = gsb_device_count();
+    for (int d = 0; d < n; d++) {
+        if (cudaSetDevice(d) != cudaSuccess || cudaDeviceReset() != cudaSuccess) {
+            const cudaError_t e = cudaGetLastError();
+            return fail(GSB_ERR_CUDA, std::string("cudaDeviceReset: ") + cudaGetErrorString(e));
+        }
+        std::lock_guard<std::mutex> lock(g_gates[d < 64 ? d : 63].mu);
+        g_gates[d < 64 ? d : 63].inflight.clear();
+        g_gates[d < 64 ? d : 63].event = nullptr;
+    }
+    cudaGetLastError();
+    return GSB_OK;
+}
+
 int gsb_next_device(uint64_t required_bytes, int* device)
 {
     static std::atomic<unsigned> next{0};

@@ -66,6 +66,14 @@ uint64_t gsb_available_device_bytes(void);
  * with more than required_bytes free (checks the device it returns — the reference checks a
  * different one); GSB_ERR_NOMEM if none. */
 int gsb_next_device(uint64_t required_bytes, int* device);
+/* HBM footprint of `rows` fingerprints of fp_bits bits uploaded with fold_factor: rows are padded to
+ * a power-of-two word count and carry a 2-byte popcount each (DESIGN.md "HBM layout").  What the
+ * fold-factor policy of the server sizes against (the reference compares raw bytes, gpusim.cpp:131-141). */
+uint64_t gsb_layout_bytes(int fp_bits, uint64_t rows, unsigned fold_factor);
+/* Last resort after a sticky CUDA error: cudaDeviceReset on every visible device.  Device state of
+ * EVERY gsb_db dies with it; each database must be put up again with gsb_db_upload (its host rows are
+ * untouched) before the next search.  gsb_server_recover does both for a server's databases. */
+int gsb_devices_reset(void);
 
 /* ---- database life cycle ------------------------------------------------------------ */
 /* reference FingerprintDB::FingerprintDB + FingerprintDBStorage ctor, .cu:117-166.
@@ -260,6 +268,9 @@ typedef struct gsb_server gsb_server;
 int gsb_server_create(const char* const* fsim_paths, int n_paths, int gpu_bitcount, int use_gpu,
                       gsb_server** out);
 void gsb_server_destroy(gsb_server* srv);
+/* After a search failed with GSB_ERR_CUDA: upload every database again, resetting the devices first if
+ * the context itself is gone.  The serve loop calls it by itself. */
+int gsb_server_recover(gsb_server* srv);
 const char* gsb_server_last_error(void);
 void gsb_server_set_use_gpu(gsb_server* srv, int use_gpu);   /* setUseGPU, gpusim.h:82          */
 int gsb_server_using_gpu(const gsb_server* srv);             /* usingGPU, gpusim.cpp:168-171    */

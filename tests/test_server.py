@@ -83,6 +83,45 @@ def test_socket_server_thread(two_dbs, small_db, tmp_path):
     assert not th.is_alive()
 
 
+def test_hostile_requests_do_not_hurt_the_daemon(two_dbs, small_db, tmp_path):
+    """a result count of 2^31-1 is clamped to the row count (no 16 GB allocation, no
+    exception through the C ABI); a request that fails (wrong query width) still gets a well-formed
+    empty response; a client that hangs up before its answer does not kill the server (MSG_NOSIGNAL)."""
+    import socket as pysocket
+    server = GPUSimServer([two_dbs[0]], use_gpu=False)
+    num, approx, smiles, ids, scores = decode_response(
+        server.handleRequest(encode_request({"small": "pass"}, 9, 2**31 - 1, 0.0, small_db[0])))
+    assert num == 9 and len(smiles) == 100                          # every row, not 2^31-1 slots
+    with pytest.raises(gsb.GsbError):
+        server.handleRequest(struct.pack(">i", 2**30) + b"\0" * 64)  # absurd database count
+    path = str(tmp_path / "hostile.sock")
+    server.listen(path)
+    th = threading.Thread(target=server.serve, args=(4,), daemon=True)
+    th.start()
+    bad = encode_request({"small": "pass"}, 77, 5, 0.0, small_db[0][:16])    # 512-bit query, 1024-bit database
+    num, approx, smiles, ids, scores = decode_response(search_over_socket(bad, path, timeout=10))
+    assert num == 77 and smiles == [] and approx == 0
+    with pysocket.socket(pysocket.AF_UNIX, pysocket.SOCK_STREAM) as c:      # hang up right after sending
+        c.connect(path)
+        c.sendall(encode_request({"small": "pass"}, 78, 100, 0.0, small_db[1]))
+    for i in range(2):                                                       # the daemon is still there
+        num, _, smiles, ids, _ = decode_response(search_over_socket(
+            encode_request({"small": "pass"}, 80 + i, 3, 0.0, small_db[0]), path, timeout=10))
+        assert num == 80 + i and ids[0] == b"ZINC00000007"
+    th.join(timeout=10)
+    assert not th.is_alive()
+
+
+def test_inconsistent_fsim_fails_at_load(tmp_path, small_fsim):
+    """a .fsim whose SMILES / id counts do not match its fingerprint count must fail when it
+    is opened, not crash the server at query time."""
+    path = str(tmp_path / "short.fsim")
+    write_fsim(path, small_fsim.fingerprints(), list(small_fsim.smiles)[:-1], list(small_fsim.ids),
+               dbkey=small_fsim.dbkey)
+    with pytest.raises(gsb.GsbError):
+        GPUSimServer([path], use_gpu=False)
+
+
 def test_server_binary_cli(two_dbs, small_db, tmp_path):
     """The Qt-free gpusimserver: reference command line (main.cpp:21-28), --cpu_only."""
     binary = os.path.join(ROOT, "gpusimilarity_b200", "gpusimserver_b200")
