@@ -226,8 +226,12 @@ def reference_cuda_leg(gsb, O, OC, np, sizes):
             t_ref.append(time.perf_counter() - t)
         ref.close()
         del ref
-        db = gsb.FingerprintDB(1024, n, "pass", chunks)
-        db.copyToGPU(1, devices=[0])
+        t = time.perf_counter()
+        db = gsb.FingerprintDB(1024, n, "pass", chunks)      # copies the chunks (as the reference ctor does), into pinned memory
+        t_create = time.perf_counter() - t
+        t = time.perf_counter()
+        db.copyToGPU(1, devices=[0])                          # DMA out of the pinned chunks + ingest kernel (layout, popcounts)
+        t_upload = time.perf_counter() - t
         for _ in range(3):
             db.search_rows(q, K, CUTOFF)
         t_own = []
@@ -241,7 +245,11 @@ def reference_cuda_leg(gsb, O, OC, np, sizes):
                     "reference_cuda_ms_min_max": [min(t_ref) * 1e3, max(t_ref) * 1e3],
                     "reference_cuda_gbs": n * ROW_BYTES / ref_ms / 1e6,
                     "b200_ms": own_ms, "b200_gbs": n * ROW_BYTES / own_ms / 1e6, "speedup": ref_ms / own_ms,
-                    "scores_identical": same})
+                    "scores_identical": same,
+                    "ingest": {"source_gb": n * ROW_BYTES / 1e9, "create_s": t_create, "upload_s": t_upload,
+                               "upload_gbs": n * ROW_BYTES / 1e9 / t_upload,
+                               "note": "gsb_db_upload: H2D straight out of the pinned host chunks + ingest_rows_kernel; "
+                                       "PCIe 5 x16 carries ~55-63 GB/s per direction"}})
         db.close()
         del db, rows, chunks
         log("reference_cuda", out[-1])
@@ -728,6 +736,9 @@ def main():
             line["single_process"] = single_process
         if reference_cuda is not None:
             line["reference_cuda"] = reference_cuda
+            ing = [r["ingest"] for r in reference_cuda if isinstance(r, dict) and "ingest" in r]
+            if ing:
+                line["ingest"] = ing[-1]
         if world == 1 and not args.no_cpu_baseline:
             try:
                 res_cpu = cpu_reference_run(3, 1, args.rows)

@@ -27,7 +27,9 @@ thread_local std::string g_fsim_err;
 
 struct Blob {
     std::vector<uint8_t> compressed;
-    std::vector<uint8_t> raw;
+    GsbHostBuf raw;            // fingerprint chunks: pinned when a CUDA device is present, the upload DMAs straight out of it
+    std::vector<uint8_t> text; // SMILES / id chunks: plain memory
+    bool is_fp = false;
     std::string error;
 };
 
@@ -68,14 +70,25 @@ struct Cursor {
 void inflate_blob(Blob* b)
 {
     if (b->compressed.size() < 4) {
-        b->raw.clear();
+        b->raw.release();
+        b->text.clear();
         return;
     }
     const uint8_t* p = b->compressed.data();
     const uLongf expected = (uLongf(p[0]) << 24) | (uLongf(p[1]) << 16) | (uLongf(p[2]) << 8) | uLongf(p[3]);
-    b->raw.resize(expected);
+    uint8_t* dst;
+    if (b->is_fp) { // inflate straight into the (pinned) buffer the upload will DMA from
+        if (!b->raw.allocate(expected)) {
+            b->error = "out of host memory";
+            return;
+        }
+        dst = b->raw.data();
+    } else {
+        b->text.resize(expected);
+        dst = b->text.data();
+    }
     uLongf got = expected;
-    const int rc = uncompress(b->raw.data(), &got, p + 4, static_cast<uLong>(b->compressed.size() - 4));
+    const int rc = uncompress(dst, &got, p + 4, static_cast<uLong>(b->compressed.size() - 4));
     if (rc != Z_OK || got != expected)
         b->error = "qUncompress failed (zlib rc " + std::to_string(rc) + ")";
     std::vector<uint8_t>().swap(b->compressed);
@@ -152,6 +165,7 @@ int gsb_fsim_open(const char* path, gsb_fsim** out)
         }
         group->resize(count);
         for (Blob& b : *group) {
+            b.is_fp = group == &f->fp;
             if (!c.bytes(&p, &n)) {
                 g_fsim_err = "truncated chunk";
                 return GSB_ERR_IO;
@@ -181,9 +195,9 @@ int gsb_fsim_open(const char* path, gsb_fsim** out)
         }
     std::string err;
     for (Blob& b : f->smi)
-        split_strings(b.raw, &f->smiles_ptrs, &err);
+        split_strings(b.text, &f->smiles_ptrs, &err);
     for (Blob& b : f->ids)
-        split_strings(b.raw, &f->id_ptrs, &err);
+        split_strings(b.text, &f->id_ptrs, &err);
     if (!err.empty()) {
         g_fsim_err = err;
         return GSB_ERR_IO;
@@ -227,7 +241,7 @@ int gsb_fsim_create_db(gsb_fsim* f, gsb_db** out)
 {
     // the database adopts the inflated fingerprint chunks (no second copy of a 100 GB database in
     // host memory); the file object keeps the SMILES / id strings
-    std::vector<std::vector<uint8_t>> chunks;
+    std::vector<GsbHostBuf> chunks;
     for (Blob& b : f->fp)
         chunks.push_back(std::move(b.raw));
     f->fp.clear();

@@ -38,6 +38,7 @@ namespace
 
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_reset_epoch{0}; // bumped by gsb_devices_reset
 
 int fail(int code, const std::string& msg)
 {
@@ -127,6 +128,7 @@ size_t padded_tile_bytes(const Layout& l, uint32_t n_tiles)
 struct SelectSet {
     gsb::ScanCtrl* ctrl = nullptr;
     unsigned int* ghist = nullptr;
+    unsigned int* ehist = nullptr; // grid-wide histogram of every appended candidate (threshold sharing)
     unsigned long long* gfinal = nullptr;
     unsigned long long* cta_keys = nullptr;
     uint32_t* cta_counts = nullptr;
@@ -201,7 +203,7 @@ struct gsb_db {
     // unfolded rows on the host, chunk by chunk as they arrived (empty for device-generated
     // shards): used by the upload, getFingerprint, search_cpu and the fold re-score
     struct HostChunk {
-        std::vector<uint8_t> bytes;
+        GsbHostBuf bytes; // pinned + mapped when a CUDA device is present (gsb_internal.h)
         uint64_t row0 = 0, n_rows = 0;
     };
     std::vector<HostChunk> host;
@@ -344,6 +346,11 @@ void gate_forget(int dev, cudaStream_t st)
 template <int W, bool RP, int CW> int launch_scan_t(const gsb::ScanParams& p, const Plan& plan, cudaStream_t st)
 {
     static thread_local int configured[64] = {0};
+    static thread_local uint64_t configured_epoch = 0;
+    if (configured_epoch != g_reset_epoch.load()) { // a device reset forgets function attributes
+        std::memset(configured, 0, sizeof(configured));
+        configured_epoch = g_reset_epoch.load();
+    }
     int dev = 0;
     GSB_CUDA(cudaGetDevice(&dev));
     auto kernel = gsb::scan_topk_kernel<W, RP, CW>;
@@ -462,6 +469,8 @@ int set_init(SelectSet& set)
     GSB_CUDA(cudaMemset(set.ctrl, 0, sizeof(gsb::ScanCtrl)));
     GSB_CUDA(cudaMalloc(&set.ghist, gsb::kBuckets * 4));
     GSB_CUDA(cudaMemset(set.ghist, 0, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMalloc(&set.ehist, gsb::kBuckets * 4));
+    GSB_CUDA(cudaMemset(set.ehist, 0, gsb::kBuckets * 4));
     GSB_CUDA(cudaMalloc(&set.gfinal, 32768 * 8));
     GSB_CUDA(cudaMalloc(&set.cta_counts, sizeof(uint32_t) * 4096));
     return GSB_OK;
@@ -492,6 +501,7 @@ int ws_recover(Shard& sh)
     for (SelectSet& set : sh.ws.sets) {
         GSB_CUDA(cudaMemset(set.ctrl, 0, sizeof(gsb::ScanCtrl)));
         GSB_CUDA(cudaMemset(set.ghist, 0, gsb::kBuckets * 4));
+        GSB_CUDA(cudaMemset(set.ehist, 0, gsb::kBuckets * 4));
     }
     if (sh.ws.bctrl)
         GSB_CUDA(cudaMemset(sh.ws.bctrl, 0, sizeof(gsb::BatchCtrl)));
@@ -553,6 +563,7 @@ void ws_free(Shard& sh)
     for (SelectSet& set : ws.sets) {
         cudaFree(set.ctrl);
         cudaFree(set.ghist);
+        cudaFree(set.ehist);
         cudaFree(set.gfinal);
         cudaFree(set.cta_keys);
         cudaFree(set.cta_counts);
@@ -652,8 +663,14 @@ int upload_rows(const gsb_db* db, Shard& sh)
     uint8_t** pinned = stg.pinned;
     uint8_t** staged = stg.staged;
     cudaEvent_t* done = stg.done;
+    // Host chunks are pinned from birth when a device is present (GsbHostBuf): the copy engine reads
+    // them in place.  Only plain-memory chunks (pinning failed) go through pinned staging buffers.
+    bool need_host_staging = false;
+    for (const gsb_db::HostChunk& hc : db->host)
+        need_host_staging |= !hc.bytes.pinned();
     for (int i = 0; i < 2; i++) {
-        GSB_CUDA(cudaMallocHost(&pinned[i], piece_rows * src_row_bytes));
+        if (need_host_staging)
+            GSB_CUDA(cudaMallocHost(&pinned[i], piece_rows * src_row_bytes));
         GSB_CUDA(cudaMalloc(&staged[i], piece_rows * src_row_bytes));
         GSB_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
     }
@@ -666,12 +683,14 @@ int upload_rows(const gsb_db* db, Shard& sh)
             const uint64_t rows = std::min<uint64_t>(piece_rows, hi_row - g0);
             GSB_CUDA(cudaEventSynchronize(done[slot])); // the previous use of this slot has been consumed
             const uint8_t* src = hc.bytes.data() + (g0 - hc.row0) * src_row_bytes;
-            uint8_t* dst = pinned[slot];
-            parallel_for(rows, [=](uint64_t lo, uint64_t hi) {
-                std::memcpy(dst + lo * src_row_bytes, src + lo * src_row_bytes, (hi - lo) * src_row_bytes);
-            });
-            GSB_CUDA(cudaMemcpyAsync(staged[slot], pinned[slot], rows * src_row_bytes, cudaMemcpyHostToDevice,
-                                     sh.ws.stream));
+            if (!hc.bytes.pinned()) {
+                uint8_t* dst = pinned[slot];
+                parallel_for(rows, [=](uint64_t lo, uint64_t hi) {
+                    std::memcpy(dst + lo * src_row_bytes, src + lo * src_row_bytes, (hi - lo) * src_row_bytes);
+                });
+                src = dst;
+            }
+            GSB_CUDA(cudaMemcpyAsync(staged[slot], src, rows * src_row_bytes, cudaMemcpyHostToDevice, sh.ws.stream));
             const uint64_t threads = rows * l.dev_words;
             gsb::ingest_rows_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, sh.ws.stream>>>(
                 reinterpret_cast<const uint32_t*>(staged[slot]), rows, g0 - sh.row_base, src_words, f, sh.tiles,
@@ -713,6 +732,7 @@ void fill_params(const gsb_db* db, Shard& sh, const Plan& plan, uint32_t k, floa
     p->cta_counts = set.cta_counts;
     p->ctrl = set.ctrl;
     p->ghist = set.ghist;
+    p->ehist = env_int("GSB_SHARE_HIST", 1) ? set.ehist : nullptr;
     p->gfinal = set.gfinal;
     p->spin_timeout_ns = spin_timeout_ns();
     p->metric = db->metric;
@@ -739,7 +759,7 @@ void print_debug_times(const std::vector<unsigned long long>& h, int grid)
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < grid; c++)
         t0 = std::min(t0, h[c * 8]);
-    const char* names[7] = {"start", "(unused)", "warp0 out of work", "cta out of work", "global histogram read",
+    const char* names[7] = {"start", "first data (warp 0)", "warp0 out of work", "cta out of work", "global histogram read",
                             "ticket", "final sort done"};
     for (int st = 0; st < 7; st++) {
         unsigned long long lo = ~0ull, hi = 0;
@@ -755,10 +775,15 @@ void print_debug_times(const std::vector<unsigned long long>& h, int grid)
             std::fprintf(stderr, "[gsb dbg] %-18s n=%3d min %8.1f us avg %8.1f us max %8.1f us\n", names[st], n, lo / 1e3,
                          sum / n / 1e3, hi / 1e3);
     }
-    unsigned long long emax = 0;
-    for (int c = 0; c < grid; c++)
-        emax = std::max(emax, h[c * 8 + 7]);
-    std::fprintf(stderr, "[gsb dbg] selects per CTA during the scan: max %llu\n", emax);
+    unsigned long long emax = 0, smax = 0;
+    double ssum = 0;
+    for (int c = 0; c < grid; c++) {
+        emax = std::max(emax, h[c * 8 + 7] & 0xffull);
+        smax = std::max(smax, h[c * 8 + 7] >> 8);
+        ssum += double(h[c * 8 + 7] >> 8);
+    }
+    std::fprintf(stderr, "[gsb dbg] selects per CTA during the scan: max %llu; time inside them (warp 0): avg %.1f us max %.1f us\n",
+                 emax, ssum / grid / 1e3, smax / 1e3);
 }
 
 // One launch per shard with a host-resident query (it travels as a kernel parameter); the last CTA
@@ -1351,7 +1376,8 @@ void unregister_host_rows(gsb_db* db)
 {
     if (db->host_registered)
         for (auto& hc : db->host)
-            cudaHostUnregister(hc.bytes.data());
+            if (!hc.bytes.pinned())
+                cudaHostUnregister(hc.bytes.data());
     db->host_registered = false;
     if (db->d_chunks)
         cudaFree(db->d_chunks);
@@ -1374,8 +1400,9 @@ void register_host_rows(gsb_db* db)
     size_t done = 0;
     bool ok = true;
     for (auto& hc : db->host) {
-        if (cudaHostRegister(hc.bytes.data(), hc.bytes.size(), cudaHostRegisterPortable | cudaHostRegisterMapped) !=
-            cudaSuccess) {
+        if (!hc.bytes.pinned() && // (pinned chunks are mapped from birth)
+            cudaHostRegister(hc.bytes.data(), hc.bytes.size(), cudaHostRegisterPortable | cudaHostRegisterMapped) !=
+                cudaSuccess) {
             ok = false;
             break;
         }
@@ -1394,7 +1421,8 @@ void register_host_rows(gsb_db* db)
         return;
     }
     for (size_t i = 0; i < done; i++)
-        cudaHostUnregister(db->host[i].bytes.data());
+        if (!db->host[i].bytes.pinned())
+            cudaHostUnregister(db->host[i].bytes.data());
     cudaGetLastError();
     std::fprintf(stderr, "[gpusim_b200] could not map the host rows for the device re-score; folded searches "
                          "re-score on the host\n");
@@ -1454,7 +1482,41 @@ int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<
 
 } // namespace
 
-int gsb_db_create_adopt(std::vector<std::vector<uint8_t>>&& chunks, int fp_bits, uint64_t fp_count, gsb_db** out)
+bool GsbHostBuf::allocate(size_t n)
+{
+    release();
+    if (n == 0)
+        return true;
+    if (env_int("GSB_PINNED_HOST", 1) && gsb_device_count() > 0) {
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, n, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
+            m_p = static_cast<uint8_t*>(p);
+            m_n = n;
+            m_pinned = true;
+            return true;
+        }
+        cudaGetLastError(); // e.g. the locked-memory limit: plain memory and the staged upload instead
+    }
+    m_p = static_cast<uint8_t*>(std::malloc(n));
+    m_n = m_p ? n : 0;
+    m_pinned = false;
+    return m_p != nullptr;
+}
+
+void GsbHostBuf::release()
+{
+    if (m_p) {
+        if (m_pinned)
+            cudaFreeHost(m_p);
+        else
+            std::free(m_p);
+    }
+    m_p = nullptr;
+    m_n = 0;
+    m_pinned = false;
+}
+
+int gsb_db_create_adopt(std::vector<GsbHostBuf>&& chunks, int fp_bits, uint64_t fp_count, gsb_db** out)
 {
     if (!out)
         return fail(GSB_ERR_INVALID, "null argument");
@@ -1556,6 +1618,7 @@ int gsb_devices_reset(void)
         g_gates[d < 64 ? d : 63].event = nullptr;
     }
     cudaGetLastError();
+    g_reset_epoch++;
     return GSB_OK;
 }
 
@@ -1580,12 +1643,21 @@ int gsb_db_create(const void* const* chunk_ptrs, const uint64_t* chunk_bytes, in
 {
     if (!out || n_chunks < 0 || (n_chunks > 0 && (!chunk_ptrs || !chunk_bytes)))
         return fail(GSB_ERR_INVALID, "null argument");
-    std::vector<std::vector<uint8_t>> chunks(n_chunks);
+    GSB_TRY
+    std::vector<GsbHostBuf> chunks(n_chunks);
     for (int c = 0; c < n_chunks; c++) { // the reference copies the chunk bytes too (.cu:123-125)
-        const uint8_t* p = static_cast<const uint8_t*>(chunk_ptrs[c]);
-        chunks[c].assign(p, p + chunk_bytes[c]);
+        if (!chunks[c].allocate(chunk_bytes[c]))
+            return fail(GSB_ERR_NOMEM, "out of host memory");
+        const uint8_t* src = static_cast<const uint8_t*>(chunk_ptrs[c]);
+        uint8_t* dst = chunks[c].data();
+        parallel_for(chunk_bytes[c] >> 12, [=](uint64_t lo, uint64_t hi) {
+            std::memcpy(dst + (lo << 12), src + (lo << 12), (hi - lo) << 12);
+        });
+        const uint64_t tail = chunk_bytes[c] & ~0xfffull;
+        std::memcpy(dst + tail, src + tail, chunk_bytes[c] - tail);
     }
     return gsb_db_create_adopt(std::move(chunks), fp_bits, fp_count, out);
+    GSB_CATCH
 }
 
 int gsb_db_create_synthetic_sharded(const int* devices, int n_devices, int fp_bits, uint64_t n_rows,
@@ -1718,9 +1790,27 @@ int gsb_db_upload(gsb_db* db, const int* devices, int n_devices, unsigned fold_f
         rc = ws_init(sh);
         if (rc)
             return rc;
-        rc = upload_rows(db, sh);
+    }
+    if (devs.size() == 1) {
+        rc = upload_rows(db, db->shards[0]);
         if (rc)
             return rc;
+    } else {
+        // every device has its own PCIe link: one host thread per shard keeps them all busy
+        std::vector<int> rcs(devs.size(), GSB_OK);
+        std::vector<std::string> errs(devs.size());
+        std::vector<std::thread> pool;
+        for (size_t i = 0; i < devs.size(); i++)
+            pool.emplace_back([db, i, &rcs, &errs]() {
+                rcs[i] = upload_rows(db, db->shards[i]);
+                if (rcs[i])
+                    errs[i] = g_err; // thread-local: carry it over to the caller's thread
+            });
+        for (auto& th : pool)
+            th.join();
+        for (size_t i = 0; i < devs.size(); i++)
+            if (rcs[i])
+                return fail(rcs[i], errs[i]);
     }
     if (f > 1) // second stage of folded searches reads the full rows in place (mapped host memory)
         register_host_rows(db);

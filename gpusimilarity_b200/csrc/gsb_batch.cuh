@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
     cs.epoch_req = &s_dummy_epoch;
     cs.hist = s_hist;
     cs.error = &s_error;
+    cs.counted = nullptr;
     unsigned long long* my_cand = p.cand + (uint64_t) blockIdx.x * nq * kBatchListCap;
     const uint32_t high_water = kBatchListCap - 32u * CW - 64u;
 
@@ -386,6 +387,7 @@ merge_batch_kernel(const unsigned long long* records, uint32_t n_ranks, uint32_t
     cs.epoch_req = &s_epoch_req;
     cs.hist = reinterpret_cast<unsigned int*>(cs.buf + cap);
     cs.error = &s_error;
+    cs.counted = nullptr;
     const uint32_t tid = threadIdx.x, j = blockIdx.x;
     if (tid == 0)
         s_error = 0;

@@ -219,6 +219,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
     cs.epoch_req = &s_dummy_epoch;
     cs.hist = reinterpret_cast<unsigned int*>(tile + (size_t) kBatchListCap * 8);
     cs.error = &s_error;
+    cs.counted = nullptr;
     unsigned long long* my_cand = p.cand + (uint64_t) blockIdx.x * nq * kBatchListCap;
 
     const bool drop_zero = p.cutoff > 0.0f; // reference .cu:265

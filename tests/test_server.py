@@ -201,3 +201,30 @@ def test_folded_server(two_dbs, small_db):
     assert server.foldFactor() == 2
     smiles, ids, scores, _ = server.searchDatabases(small_db[0], 5, 0.0, {"small": "pass"})
     assert ids[0] == b"ZINC00000007" and scores[0] == 1.0
+
+
+@pytest.mark.gpu
+def test_daemon_recovers_after_device_reset(two_dbs, small_db, tmp_path):
+    """the daemon's way back after GSB_ERR_CUDA — gsb_server_recover puts the databases
+    up again, after a cudaDeviceReset if need be.  Runs in its own process: the reset takes the whole
+    CUDA context of the process with it."""
+    script = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r})
+from gpusimilarity_b200._lib import lib, check
+from gpusimilarity_b200.server import GPUSimServer
+from gpusimilarity_b200.fsim import read_fsim
+db = read_fsim({two_dbs[0]!r}).fingerprints()
+srv = GPUSimServer([{two_dbs[0]!r}, {two_dbs[1]!r}])
+names = {{"small": "pass", "small_copy": "pass"}}
+want = srv.searchDatabases(db[3], 10, 0.0, names)
+assert lib().gsb_server_recover(srv._h) == 0                      # plain re-upload
+assert srv.searchDatabases(db[3], 10, 0.0, names) == want
+check(lib().gsb_devices_reset())                                  # the context is gone ...
+assert lib().gsb_server_recover(srv._h) == 0                      # ... and the databases come back
+assert srv.searchDatabases(db[3], 10, 0.0, names) == want
+assert srv.searchDatabases(db[0], 10, 0.3, {{"small": "pass"}})[3] == 3
+print("recovered")
+"""
+    r = subprocess.run([os.sys.executable, "-c", script], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "recovered" in r.stdout, r.stdout + r.stderr
