@@ -20,11 +20,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+#include <sys/mman.h>
 
 #if defined(__x86_64__)
 #include <immintrin.h>
@@ -186,6 +188,7 @@ struct Shard {
     uint8_t* tiles = nullptr;
     size_t bytes = 0;
     Workspace ws;
+    uint64_t epoch = 0; // g_reset_epoch when the handles were made: a device reset leaves them dangling
 };
 
 struct Plan {
@@ -232,6 +235,7 @@ struct gsb_db {
     gsb::RescoreChunk* d_chunks = nullptr; // chunk table on the re-score device (shard 0's)
     unsigned long long* rescore_host = nullptr, *rescore_dev = nullptr; // mapped pinned: candidates in, keys out
     size_t rescore_cap = 0;
+    uint64_t rescore_epoch = 0; // g_reset_epoch when the above were made
     // queries in flight through the host-buffer API (gsb_db_search_async / _wait)
     struct Pending {
         uint64_t ticket = 0; // 0 = free
@@ -479,6 +483,7 @@ int set_init(SelectSet& set)
 int ws_init(Shard& sh)
 {
     Workspace& ws = sh.ws;
+    sh.epoch = g_reset_epoch.load();
     GSB_CUDA(cudaSetDevice(sh.device));
     GSB_CUDA(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking));
     for (SelectSet& set : ws.sets) {
@@ -551,6 +556,10 @@ int ws_reserve(Shard& sh, uint32_t k, int grid, int slot)
 
 void ws_free(Shard& sh)
 {
+    if (sh.epoch != g_reset_epoch.load()) { // cudaDeviceReset took every stream, event and allocation
+        sh = Shard();                       // with it; the stale handles must not reach the runtime again
+        return;
+    }
     cudaSetDevice(sh.device);
     Workspace& ws = sh.ws;
     if (ws.stream) {
@@ -732,7 +741,7 @@ void fill_params(const gsb_db* db, Shard& sh, const Plan& plan, uint32_t k, floa
     p->cta_counts = set.cta_counts;
     p->ctrl = set.ctrl;
     p->ghist = set.ghist;
-    p->ehist = env_int("GSB_SHARE_HIST", 1) ? set.ehist : nullptr;
+    p->ehist = env_int("GSB_SHARE_HIST", 0) ? set.ehist : nullptr; // opt-in: fewer selects, same throughput (profiles/r02_fixed_cost.md)
     p->gfinal = set.gfinal;
     p->spin_timeout_ns = spin_timeout_ns();
     p->metric = db->metric;
@@ -1374,15 +1383,16 @@ float score_cpu(const gsb_db* db, const uint32_t* q, const uint32_t* d, uint32_t
 // ---- folded search, second stage on the device ------------------------------------------------
 void unregister_host_rows(gsb_db* db)
 {
-    if (db->host_registered)
+    const bool stale = db->rescore_epoch != g_reset_epoch.load(); // a device reset freed all of it already
+    if (db->host_registered && !stale)
         for (auto& hc : db->host)
             if (!hc.bytes.pinned())
                 cudaHostUnregister(hc.bytes.data());
     db->host_registered = false;
-    if (db->d_chunks)
+    if (db->d_chunks && !stale)
         cudaFree(db->d_chunks);
     db->d_chunks = nullptr;
-    if (db->rescore_host)
+    if (db->rescore_host && !stale)
         cudaFreeHost(db->rescore_host);
     db->rescore_host = db->rescore_dev = nullptr;
     db->rescore_cap = 0;
@@ -1395,6 +1405,7 @@ void register_host_rows(gsb_db* db)
 {
     if (db->host_registered || db->host.empty() || db->shards.empty() || env_int("GSB_FOLD_RESCORE_HOST", 0))
         return;
+    db->rescore_epoch = g_reset_epoch.load();
     cudaSetDevice(db->shards[0].device);
     std::vector<gsb::RescoreChunk> table;
     size_t done = 0;
@@ -1482,34 +1493,54 @@ int fetch_rows(const gsb_db* db, const std::vector<uint64_t>& rows, std::vector<
 
 } // namespace
 
+// Pinned buffers are plain (huge-page advised) memory that is page-locked with cudaHostRegister, not
+// cudaHostAlloc memory: the rows must outlive a cudaDeviceReset (gsb_devices_reset re-registers
+// every live buffer from this table; cudaHostAlloc memory would be unmapped with the context).
+namespace {
+std::mutex g_hostbuf_mu;
+std::map<void*, size_t> g_hostbufs; // live registered buffers
+} // namespace
+
 bool GsbHostBuf::allocate(size_t n)
 {
     release();
     if (n == 0)
         return true;
-    if (env_int("GSB_PINNED_HOST", 1) && gsb_device_count() > 0) {
-        void* p = nullptr;
-        if (cudaHostAlloc(&p, n, cudaHostAllocPortable | cudaHostAllocMapped) == cudaSuccess) {
-            m_p = static_cast<uint8_t*>(p);
-            m_n = n;
-            m_pinned = true;
-            return true;
-        }
-        cudaGetLastError(); // e.g. the locked-memory limit: plain memory and the staged upload instead
-    }
-    m_p = static_cast<uint8_t*>(std::malloc(n));
-    m_n = m_p ? n : 0;
+    void* p = nullptr;
+    const size_t align = n >= (2u << 20) ? (2u << 20) : 4096;
+    if (posix_memalign(&p, align, n) != 0)
+        return false;
+#ifdef MADV_HUGEPAGE
+    if (align > 4096)
+        madvise(p, n, MADV_HUGEPAGE); // 512 x fewer pages to fault and lock
+#endif
+    m_p = static_cast<uint8_t*>(p);
+    m_n = n;
     m_pinned = false;
-    return m_p != nullptr;
+    if (env_int("GSB_PINNED_HOST", 1) && gsb_device_count() > 0) {
+        if (cudaHostRegister(p, n, cudaHostRegisterPortable | cudaHostRegisterMapped) == cudaSuccess) {
+            m_pinned = true;
+            std::lock_guard<std::mutex> lock(g_hostbuf_mu);
+            g_hostbufs[p] = n;
+        } else {
+            cudaGetLastError(); // e.g. the locked-memory limit: plain memory and the staged upload instead
+        }
+    }
+    return true;
 }
 
 void GsbHostBuf::release()
 {
     if (m_p) {
-        if (m_pinned)
-            cudaFreeHost(m_p);
-        else
-            std::free(m_p);
+        if (m_pinned) {
+            {
+                std::lock_guard<std::mutex> lock(g_hostbuf_mu);
+                g_hostbufs.erase(m_p);
+            }
+            if (cudaHostUnregister(m_p) != cudaSuccess)
+                cudaGetLastError();
+        }
+        std::free(m_p);
     }
     m_p = nullptr;
     m_n = 0;
@@ -1619,6 +1650,15 @@ int gsb_devices_reset(void)
     }
     cudaGetLastError();
     g_reset_epoch++;
+    if (n > 0) { // the reset dropped every page-lock: put the host rows back under it
+        cudaSetDevice(0);
+        std::lock_guard<std::mutex> lock(g_hostbuf_mu);
+        for (auto& kv : g_hostbufs)
+            if (cudaHostRegister(kv.first, kv.second, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+                const cudaError_t e = cudaGetLastError();
+                return fail(GSB_ERR_CUDA, std::string("re-registering host rows after the reset: ") + cudaGetErrorString(e));
+            }
+    }
     return GSB_OK;
 }
 

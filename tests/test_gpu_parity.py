@@ -315,7 +315,8 @@ def test_tuning_knobs_do_not_change_results(monkeypatch):
     want = OC.c_search(q, rows_np, 1000, 0.0)
     for env in ({"GSB_STAGES": "2"}, {"GSB_STAGES": "4", "GSB_WARPS": "8"}, {"GSB_GRID": "7"},
                 {"GSB_GRID": "1", "GSB_WARPS": "12"}, {"GSB_ROWPOP": "0", "GSB_WARPS": "4"},
-                {"GSB_ROWPOP": "0"}, {"GSB_MIN_CAP": "8192", "GSB_WARPS": "8"}):
+                {"GSB_ROWPOP": "0"}, {"GSB_MIN_CAP": "8192", "GSB_WARPS": "8"}, {"GSB_SHARE_HIST": "1"},
+                {"GSB_SHARE_HIST": "1", "GSB_GRID": "9"}, {"GSB_PDL": "0"}, {"GSB_PDL": "0", "GSB_SHARE_HIST": "1"}):
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
         db = make_db(rows_np)
@@ -323,6 +324,21 @@ def test_tuning_knobs_do_not_change_results(monkeypatch):
         db.close()
         for k_ in env:
             monkeypatch.delenv(k_)
+
+
+def test_grid_wide_threshold_sharing(monkeypatch):
+    """GSB_SHARE_HIST=1: every candidate that goes through a select is counted in a grid-wide histogram
+    whose k-th bucket bounds the threshold of every CTA.  3 M rows (every SM busy), ties, cutoffs, k up
+    to the peeling passes (key ceiling), repeated queries (the histogram must be left clean)."""
+    monkeypatch.setenv("GSB_SHARE_HIST", "1")
+    n = 3_000_000
+    rows_np = OC.c_synth_db(4711, n, 32, 1500)
+    rows_np[500_000:500_900] = rows_np[9]                          # a tie group close to k
+    db = make_db(rows_np)
+    for rep in range(2):
+        for q in (O.synth_template(4711, 32), rows_np[9], rows_np[n - 1]):
+            for k, cutoff in ((1000, 0.0), (10, 0.0), (1000, 0.12), (3000, 0.0), (20000, 0.0)):
+                check(db, rows_np, q, k, cutoff, f"shared thresholds rep {rep}")
 
 
 def test_synthetic_device_generator_matches_host_twin():

@@ -209,7 +209,8 @@ def test_daemon_recovers_after_device_reset(two_dbs, small_db, tmp_path):
     up again, after a cudaDeviceReset if need be.  Runs in its own process: the reset takes the whole
     CUDA context of the process with it."""
     script = f"""
-import sys, numpy as np
+import sys, faulthandler, numpy as np
+faulthandler.enable()                                             # a crash names the step it happened in
 sys.path.insert(0, {ROOT!r})
 from gpusimilarity_b200._lib import lib, check
 from gpusimilarity_b200.server import GPUSimServer
