@@ -7,7 +7,7 @@ LIB    := gpusimilarity_b200/libgpusim_b200.so
 
 all: $(LIB) adapter oracle
 
-$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/gsb_sliced.cuh $(CSRC)/gsb_sliced_math.h $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
+$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/gsb_sliced.cuh $(CSRC)/gsb_sliced_math.h $(CSRC)/gsb_tensor.cuh $(CSRC)/gsb_tensor_math.h $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp -lz
 
 # gpusimserver without Qt: same command line as the reference's main.cpp (--cpu_only, --gpu_bitcount)

@@ -8,6 +8,7 @@
 #include "gsb_batch.cuh"
 #include "gsb_kernels.cuh"
 #include "gsb_sliced.cuh"
+#include "gsb_tensor.cuh"
 
 #include "../../include/gpusim_b200.h"
 #include "gsb_internal.h"
@@ -987,30 +988,48 @@ int scan_topk(const gsb_db* db, const uint32_t* q_dev_words, uint64_t k_total, f
 
 // ---- multi-query kernel ------------------------------------------------------------------
 // Which multi-query kernel serves a batch.  GSB_BATCH_KERNEL: 0 = none (loop over the single-query
-// kernel), 1 = automatic (default), 2 = POPC kernel, 3 = bit-sliced kernel wherever it applies.
-enum BatchKernel { kBatchNone = 0, kBatchPopc = 1, kBatchSliced = 2 };
+// kernel), 1 = automatic (default), 2 = POPC kernel, 3 = bit-sliced kernel wherever it applies,
+// 4 = tensor-core kernel wherever it applies.
+enum BatchKernel { kBatchNone = 0, kBatchPopc = 1, kBatchSliced = 2, kBatchTensor = 3 };
 
-BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, float cutoff)
+// Cost model of the automatic choice between the bit-sliced and the tensor-core kernel, in
+// milliseconds per 10^9 rows on one B200 (profiles/r02_tensor.md): the bit-sliced kernel pays per
+// set bit of the batch, the tensor-core kernel per group of 128 queries.
+constexpr double kSlicedMsBase = 50.0, kSlicedMsPerSetBit = 7.6e-3, kTensorMsPerGroup = 80.0;
+
+// set_bits: set bits of all queries of the batch together (-1 = not known: queries in device memory)
+BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, float cutoff, int64_t set_bits = -1)
 {
     const int mode = env_int("GSB_BATCH_KERNEL", 1);
     if (mode == 0 || !db->layout.rowpop || db->layout.dev_words > 32 || k < 1 || k > gsb::kMaxBatchK || n_queries < 2)
         return kBatchNone;
     if (mode == 2)
         return kBatchPopc;
+    const bool tensor_ok = db->metric == gsb::kMetricTanimoto && db->layout.dev_words == 32;
+    if (mode == 4 && tensor_ok)
+        return kBatchTensor;
     if (mode == 3 && db->metric == gsb::kMetricTanimoto)
         return kBatchSliced;
     if (db->metric != gsb::kMetricTanimoto)
-        return kBatchPopc; // the bit-sliced kernel's filter bound is Tanimoto's
+        return kBatchPopc; // the filter bound of the other two kernels is Tanimoto's
     // The bit-sliced kernel pays a transposition per tile: measured cross-over between 4 and 8
     // queries (profiles/r01_sweep.md).  (A low positive cutoff sends many rows through its exact
     // path, but even with every row on that path it stays ahead of the POPC kernel.)
     (void) cutoff;
-    return n_queries >= 6 ? kBatchSliced : kBatchPopc;
+    if (n_queries < 6)
+        return kBatchPopc;
+    if (tensor_ok && set_bits >= 0 && mode == 1 && env_int("GSB_TENSOR_AUTO", 1)) {
+        const double sliced = kSlicedMsBase + kSlicedMsPerSetBit * static_cast<double>(set_bits);
+        const double tensor = kTensorMsPerGroup * ((n_queries + gsb::kTcQueries - 1) / gsb::kTcQueries);
+        if (tensor < sliced)
+            return kBatchTensor;
+    }
+    return kBatchSliced;
 }
 
 uint32_t batch_max_queries(BatchKernel which)
 {
-    return which == kBatchSliced ? gsb::kMaxSlicedQueries : gsb::kMaxBatchQueries;
+    return which == kBatchPopc ? gsb::kMaxBatchQueries : gsb::kMaxSlicedQueries;
 }
 
 struct BatchPlan {
@@ -1244,6 +1263,57 @@ int sliced_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     return GSB_OK;
 }
 
+// Tensor-core kernel over one shard (gsb_tensor.cuh): one launch per group of 128 queries, all
+// queued on `st`.  The groups share the per-shard workspace; launches of one stream run one after
+// the other and the last CTA of each leaves the control block clean for the next.
+int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint32_t* d_queries, uint32_t nq, uint32_t k,
+                        float cutoff, unsigned long long* out_keys, uint32_t* out_n, unsigned long long* out_surv)
+{
+    int smem_max = 0, sms = 0;
+    int rc = smem_limit(sh.device, &smem_max);
+    if (rc)
+        return rc;
+    GSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sh.device));
+    const uint32_t smem = gsb::tc_smem_bytes();
+    if (db->layout.dev_words != 32 || !db->layout.rowpop || db->layout.tile_bytes != gsb::kTcRawBatch)
+        return fail(GSB_ERR_INVALID, "the tensor-core multi-query kernel handles 1024-bit rows with popcount trailers");
+    if (smem + 2048 > static_cast<uint32_t>(smem_max))
+        return fail(GSB_ERR_INVALID, "the tensor-core multi-query kernel does not fit this device's shared memory");
+    const uint32_t n_tiles = (sh.n_tiles + gsb::kTcTileBatches - 1) / gsb::kTcTileBatches;
+    int grid = std::max(1, std::min<int>(sms, n_tiles)); // all CTAs resident: grid-wide arrival counter
+    if (const int g = env_int("GSB_GRID", 0))
+        grid = std::max(1, std::min(grid, g));
+    rc = batch_reserve(sh, db->layout, k, grid, std::min<uint32_t>(nq, gsb::kTcQueries));
+    if (rc)
+        return rc;
+    rc = sliced_reserve(sh); // thresholds and score histograms are the bit-sliced kernel's
+    if (rc)
+        return rc;
+    Workspace& ws = sh.ws;
+    GSB_CUDA(cudaSetDevice(sh.device));
+    rc = gate_launch(sh.device, ws, st, grid);
+    if (rc)
+        return rc;
+    void* kernel = reinterpret_cast<void*>(gsb::scan_tensor_kernel);
+    GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));
+    GSB_CUDA(cudaMemsetAsync(ws.stau, 0, static_cast<size_t>(nq) * sizeof(unsigned long long), st));
+    for (uint32_t q0 = 0; q0 < nq; q0 += gsb::kTcQueries) {
+        const uint32_t n = std::min<uint32_t>(gsb::kTcQueries, nq - q0);
+        gsb::TensorParams tp;
+        std::memset(&tp, 0, sizeof(tp));
+        fill_batch_params(db, sh, n, k, cutoff, d_queries + static_cast<size_t>(q0) * 32, out_keys + static_cast<size_t>(q0) * k,
+                          out_n + q0, out_surv + q0, &tp.b);
+        tp.ghist = ws.shist + static_cast<size_t>(q0) * gsb::kSlicedHistBuckets;
+        tp.gtau = ws.stau + q0;
+        tp.n_tiles = n_tiles;
+        void* args[] = {&tp};
+        GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(gsb::kTcThreads), args, smem, st));
+        g_launches++;
+    }
+    return GSB_OK;
+}
+
 // One pass over one shard for nq <= batch_max_queries(which) queries already in device memory.
 // Results: out_keys [nq][k], out_survivors [nq], out_n [nq].
 int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, BatchKernel which, const uint32_t* d_queries,
@@ -1252,6 +1322,8 @@ int batch_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, BatchKernel
 {
     if (which == kBatchSliced)
         return sliced_launch_shard(db, sh, st, d_queries, nq, k, cutoff, out_keys, out_n, out_surv);
+    if (which == kBatchTensor)
+        return tensor_launch_shard(db, sh, st, d_queries, nq, k, cutoff, out_keys, out_n, out_surv);
     BatchPlan plan;
     int rc = make_batch_plan(db->layout, sh, &plan);
     if (rc)
@@ -2106,8 +2178,12 @@ int gsb_db_search_batch(const gsb_db* db, const int32_t* query_words, int n_word
     std::lock_guard<std::mutex> lock(db->mu);
     // folded rows: the scan pulls k * F * floor(log2 2F) candidates per query (reference .cu:284-287)
     const uint64_t k_scan = db->fold_factor == 1 ? k : scan_candidates(db, k);
-    const BatchKernel which =
-        k_scan <= gsb::kMaxBatchK ? batch_kernel_choice(db, static_cast<uint32_t>(k_scan), n_queries, cutoff) : kBatchNone;
+    int64_t set_bits = 0; // (of the unfolded queries: an upper bound of what the scan sees)
+    for (size_t i = 0; i < static_cast<size_t>(n_queries) * n_words; i++)
+        set_bits += __builtin_popcount(static_cast<uint32_t>(query_words[i]));
+    const BatchKernel which = k_scan <= gsb::kMaxBatchK
+                                  ? batch_kernel_choice(db, static_cast<uint32_t>(k_scan), n_queries, cutoff, set_bits)
+                                  : kBatchNone;
     if (which != kBatchNone) {
         std::vector<std::vector<unsigned long long>> merged;
         std::vector<uint64_t> approx;
@@ -2153,7 +2229,10 @@ int gsb_db_batch_mode(const gsb_db* db, uint32_t k, int n_queries, float cutoff,
     const uint64_t k_scan = db->fold_factor == 1 ? k : scan_candidates(db, k);
     const BatchKernel which =
         k_scan <= gsb::kMaxBatchK ? batch_kernel_choice(db, static_cast<uint32_t>(k_scan), n_queries, cutoff) : kBatchNone;
-    *mode = which == kBatchSliced ? GSB_BATCH_SLICED : (which == kBatchPopc ? GSB_BATCH_POPC : GSB_BATCH_LOOPED);
+    *mode = which == kBatchSliced   ? GSB_BATCH_SLICED
+            : which == kBatchTensor ? GSB_BATCH_TENSOR
+            : which == kBatchPopc   ? GSB_BATCH_POPC
+                                    : GSB_BATCH_LOOPED;
     if (queries_per_pass)
         *queries_per_pass = which == kBatchNone ? 1u : batch_max_queries(which);
     return GSB_OK;

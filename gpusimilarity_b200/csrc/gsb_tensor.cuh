@@ -1,0 +1,551 @@
+// Tensor-core multi-query scan for 1024-bit rows: the common-bit counts of 128 queries x 128 rows
+// per tile come out of tcgen05.mma (kind::i8) instead of the CUDA cores, so the cost of a pass no
+// longer depends on how many bits the queries have set (the bit-sliced kernel, gsb_sliced.cuh, pays
+// per set bit and wins for sparse queries; the host picks by the batch's set-bit total).
+//
+//   common = popc(q & d)  (reference TanimotoFunctor, fingerprintdb_cuda.cu:97-98)
+//          = dot product of the two bit vectors: D[128 queries][128 rows] += A[128 x K] * B[K x 128]
+// with K = 1024 bit positions expanded to bytes (gsb_tensor_math.h: 2^plane on the row side,
+// 2^(7-plane) on the query side, D = 128 * common exactly in s32).  HBM keeps the packed rows
+// (130 B per row and pass); the expansion happens on the way through shared memory.
+//
+// One CTA per SM, 20 warps, warp-specialised:
+//   warp 0        TMA producer: 128-row tiles (4 batches of 32 rows + popcount trailers) into a raw ring
+//   warps 4-11    expanders: a warp keeps 16 raw rows in registers (lane = row word) and writes the
+//                 four quarter-K slabs of the tile (bit planes 2g, 2g+1) as the B operand: canonical
+//                 K-major core matrices without swizzle, 8-byte stores, bank-conflict free
+//   warp 1        MMA issuer (one thread): 8 x tcgen05.mma M128 N128 K32 per slab, A = the queries
+//                 resident in tensor memory (256 columns, written once), D double-buffered in the
+//                 other 256 columns; tcgen05.commit releases slabs and publishes accumulators
+//   warps 12-19   epilogue: tcgen05.ld the accumulators (lane = query, column = row), one FMA +
+//                 compare per value against the query's running threshold (tc_filter_*); the rare
+//                 values that pass are scored exactly (tanimoto_div, popcount trailer) and appended
+//                 to the query's candidate list — same keys, cutoff and survivor rules, select
+//                 rounds and end of launch as the other multi-query kernels (gsb_batch.cuh)
+//   warp 2        turns the grid-wide candidate score histograms of "its" queries into thresholds
+//                 and publishes them (as share_thresholds of the bit-sliced kernel)
+// A launch takes up to 128 queries; larger batches are one launch per 128 queries.
+#pragma once
+
+#include "gsb_sliced.cuh"
+#include "gsb_tensor_math.h"
+
+namespace gsb
+{
+
+constexpr uint32_t kTcSlabRing = 4;   // expanded slabs in flight (one tile)
+constexpr uint32_t kTcRawRing = 3;    // raw tiles in flight
+constexpr uint32_t kTcPdRing = 8;     // tiles whose row popcounts are kept: the expanders run up to 4 tiles ahead of the epilogue
+constexpr uint32_t kTcRawBatch = kBatchRows * 128u + kBatchRows * 2u; // 4160: 32 rows + u16 popcounts
+constexpr uint32_t kTcRawStage = kTcTileBatches * kTcRawBatch;        // 16640
+constexpr int kTcWarps = 20, kTcThreads = kTcWarps * 32;
+constexpr int kTcExpWarp0 = 4, kTcExpWarps = 8, kTcEpiWarp0 = 12, kTcEpiWarps = 8, kTcEpiThreads = kTcEpiWarps * 32;
+constexpr uint32_t kTcTmemCols = 512, kTcTmemD = 256; // columns [0,256): queries, [256,512): two accumulator tiles
+constexpr uint32_t kTcPruneMin = 64, kTcWarpSortMax = 64;
+
+__host__ __device__ constexpr uint32_t tc_smem_bytes()
+{
+    return kTcSlabRing * kTcSlabBytes + kTcRawRing * kTcRawStage + kBatchListCap * 8u + kBuckets * 4u +
+           kTcPdRing * kTcTileRows * 4u + kTcQueries * (8u + 8u + 4u + 4u);
+}
+
+struct TensorParams {
+    BatchParams b;            // database, k, cutoff, nq (<= 128), candidate lists, outputs
+    unsigned int* ghist;      // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
+    unsigned long long* gtau; // [nq] thresholds shared by all CTAs; zero on entry
+    uint32_t n_tiles;         // 128-row tiles of the shard
+};
+
+// ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) --------------------------------------------------
+__device__ __forceinline__ void tc_fence_before()
+{
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after()
+{
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor]; u8 x u8 -> s32
+__device__ __forceinline__ void tc_mma_i8_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate)
+{
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&a)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(a[0]),
+                 "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+                 "%14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+// Shared-memory matrix descriptor: K-major, no swizzle (core matrix = 8 rows x 16 bytes, contiguous),
+// leading byte offset = distance of the two 16-byte chunks of a K-step, stride byte offset =
+// distance of consecutive 8-row groups; bits 46-47 = descriptor version 1 (sm_100).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr)
+{
+    return static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4) | (static_cast<uint64_t>(kTcLbo >> 4) << 16) |
+           (static_cast<uint64_t>(kTcSbo >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor, kind::i8: D = s32 (bits 4-5 = 2), A and B unsigned 8 bit (bits 7-12 = 0),
+// both K-major (bits 15, 16 = 0), N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t kTcIdesc = (2u << 4) | ((kTcTileRows >> 3) << 17) | ((kTcQueries >> 4) << 24);
+
+// Pipeline wait with a way out: never hangs and never traps.  A wait that outlasts the launch's spin
+// bound raises kErrPipeline (reported like a grid-barrier timeout: every count becomes
+// GSB_COUNT_ERROR) and sets the abort flag, after which every wait of every role returns at once,
+// so the CTA runs to its end and the context stays usable.
+__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
+                                        unsigned int* error, unsigned long long timeout_ns)
+{
+    if (mbar_try_wait(bar, parity))
+        return;
+    const unsigned long long t0 = global_ns();
+    for (uint32_t spins = 0;; spins++) {
+        if (mbar_try_wait(bar, parity))
+            return;
+        if ((spins & 63u) == 63u) {
+            if (*abort_flag)
+                return;
+            if (global_ns() - t0 > timeout_ns) {
+                atomicOr(error, kErrPipeline);
+                *abort_flag = 1;
+                return;
+            }
+        }
+    }
+}
+
+// Everything the exact path of one (query, row) pair needs; lives in local memory, the path is rare.
+struct TcExact {
+    const BatchParams* p;
+    unsigned long long* list;       // this CTA's candidate list of the query
+    volatile unsigned long long* tau;
+    unsigned long long* surv;
+    unsigned int* cnt;
+    unsigned int* need_select;
+    unsigned int* error;
+    unsigned int* ghist;            // the query's row of the grid-wide histogram
+    uint32_t pq, row0, row_base32;  // query popcount, first row of the tile (shard numbering), shard base
+    bool drop_zero;
+};
+
+__device__ __noinline__ void tc_exact(const TcExact& e, uint32_t d, uint32_t col, float pdf)
+{
+    const BatchParams& p = *e.p;
+    const uint32_t common = d >> 7, pd = static_cast<uint32_t>(pdf), row_local = e.row0 + col;
+    if (row_local >= p.n_rows)
+        return;
+    // reference .cu:100-102: IEEE divide, then the cutoff test (NaN -> 0)
+    float score = tanimoto_div(common, e.pq + pd - common);
+    score = (score >= p.cutoff) ? score : 0.0f;
+    if (e.drop_zero) { // .cu:265-271
+        if (score == 0.0f)
+            return;
+        atomicAdd(e.surv, 1ull);
+    }
+    const unsigned long long key = (static_cast<unsigned long long>(__float_as_uint(score)) << 32) |
+                                   static_cast<unsigned long long>(0xffffffffu - (e.row_base32 + row_local));
+    if (!(key > *e.tau))
+        return;
+    const unsigned idx = atomicAdd(e.cnt, 1u);
+    if (idx + 1 > kBatchListCap / 2)
+        *reinterpret_cast<volatile unsigned int*>(e.need_select) = 1; // cut the list back at the next tile boundary
+    if (idx < kBatchListCap)
+        e.list[idx] = key;
+    else
+        atomicOr(e.error, kErrOverflow);
+    atomicAdd(&e.ghist[sliced_bucket(__float_as_uint(score))], 1u);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid_constant__ TensorParams tp)
+{
+    constexpr uint32_t kFull = 0xffffffffu;
+    const BatchParams& p = tp.b;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t s_raw_full[kTcRawRing], s_raw_empty[kTcRawRing], s_slab_full[kTcSlabRing],
+        s_slab_empty[kTcSlabRing], s_tmem_full[2], s_tmem_empty[2], s_pd_full[kTcPdRing];
+    __shared__ uint32_t s_tmem_base;
+    __shared__ unsigned long long s_stage_tau;
+    __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_need_select, s_error, s_done, s_abort;
+
+#define TC_WAIT(bar, parity) tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns)
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t nq = p.nq;
+    // shared memory carve-up
+    uint8_t* slabs = smem;
+    uint8_t* raw = slabs + kTcSlabRing * kTcSlabBytes;
+    uint8_t* stage = raw + kTcRawRing * kTcRawStage;
+    float* s_pdf = reinterpret_cast<float*>(stage + kBatchListCap * 8u + kBuckets * 4u); // [kTcPdRing][128]
+    unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_pdf + kTcPdRing * kTcTileRows); // [128]
+    unsigned long long* s_surv = s_tau + kTcQueries;
+    unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_surv + kTcQueries);
+    unsigned int* s_flags = s_cnt + kTcQueries;
+    CandShared cs;
+    cs.buf = reinterpret_cast<unsigned long long*>(stage);
+    cs.cap = kBatchListCap;
+    cs.count = &s_stage_count;
+    cs.tau = &s_stage_tau;
+    cs.epoch_req = &s_dummy_epoch;
+    cs.hist = reinterpret_cast<unsigned int*>(stage + kBatchListCap * 8u);
+    cs.error = &s_error;
+    cs.counted = nullptr;
+    unsigned long long* my_cand = p.cand + (uint64_t) blockIdx.x * nq * kBatchListCap;
+
+    // this CTA's tiles: blockIdx.x, blockIdx.x + grid, ... (every role derives the same sequence)
+    const uint32_t n_local = blockIdx.x < tp.n_tiles ? (tp.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+
+    for (uint32_t j = tid; j < kTcQueries; j += kTcThreads) {
+        s_tau[j] = 0;
+        s_surv[j] = 0;
+        s_cnt[j] = 0;
+        s_flags[j] = 0;
+    }
+    if (tid == 0) {
+        for (uint32_t i = 0; i < kTcRawRing; i++) {
+            mbar_init(&s_raw_full[i], 1);
+            mbar_init(&s_raw_empty[i], kTcExpWarps);
+        }
+        for (uint32_t i = 0; i < kTcSlabRing; i++) {
+            mbar_init(&s_slab_full[i], kTcExpWarps);
+            mbar_init(&s_slab_empty[i], 1);
+        }
+        for (uint32_t i = 0; i < 2; i++) {
+            mbar_init(&s_tmem_full[i], 1);
+            mbar_init(&s_tmem_empty[i], kTcEpiWarps);
+        }
+        for (uint32_t i = 0; i < kTcPdRing; i++)
+            mbar_init(&s_pd_full[i], kTcExpWarps);
+        mbar_fence_init();
+        s_alive = 0;
+        s_need_select = 0;
+        s_error = 0;
+        s_done = 0;
+        s_abort = 0;
+    }
+    if (warp == 1) { // tensor memory: all 512 columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                     "n"(kTcTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = s_tmem_base;
+
+    // ---- the queries become the A operand: thread = query = lane of tensor memory
+    uint32_t pq = 0;
+    const uint32_t ew = warp - kTcEpiWarp0;           // epilogue warp number (valid for warps >= 12)
+    const uint32_t quarter = warp & 3u;               // the tensor-memory lanes a warp may touch: 32 * (warp % 4)
+    const uint32_t qj = quarter * 32u + lane;         // the query of an epilogue thread
+    if (warp >= kTcEpiWarp0) {
+        uint32_t wq[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+            wq[i] = qj < nq ? __ldg(&p.queries[(size_t) qj * 32 + i]) : 0u;
+#pragma unroll
+        for (int i = 0; i < 32; i++)
+            pq += __popc(wq[i]);
+        if (ew < 4) {
+#pragma unroll
+            for (uint32_t ks = 0; ks < kTcSlabs * kTcSlabSteps; ks++) {
+                uint32_t a[8];
+#pragma unroll
+                for (uint32_t u = 0; u < 8; u++) {
+                    uint32_t iw = 0, plane = 0;
+                    tc_a_source(ks, u, &iw, &plane);
+                    a[u] = tc_query_word(wq[iw], plane);
+                }
+                tc_st8(tmem + ((quarter * 32u) << 16) + ks * 8u, a);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (uint32_t n = 0; n < n_local; n++) {
+                const uint32_t t = blockIdx.x + n * gridDim.x, slot = n % kTcRawRing, use = n / kTcRawRing;
+                TC_WAIT(&s_raw_empty[slot], (use & 1u) ^ 1u);
+                const uint32_t b0 = t * kTcTileBatches;
+                const uint32_t nb = p.n_batches - b0 < kTcTileBatches ? p.n_batches - b0 : kTcTileBatches;
+                mbar_arrive_expect_tx(&s_raw_full[slot], nb * kTcRawBatch);
+                for (uint32_t b = 0; b < nb; b++)
+                    tma_bulk_g2s(raw + slot * kTcRawStage + b * kTcRawBatch, p.tiles + (uint64_t)(b0 + b) * p.batch_stride,
+                                 kTcRawBatch, &s_raw_full[slot]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            for (uint32_t n = 0; n < n_local; n++) {
+                const uint32_t buf = n & 1u;
+                TC_WAIT(&s_tmem_empty[buf], ((n >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator tile
+                tc_fence_after();
+                const uint32_t d_tmem = tmem + kTcTmemD + buf * kTcTileRows;
+                for (uint32_t g = 0; g < kTcSlabs; g++) {
+                    const uint32_t s = n * kTcSlabs + g, slot = s % kTcSlabRing;
+                    TC_WAIT(&s_slab_full[slot], (s / kTcSlabRing) & 1u);
+                    tc_fence_after();
+                    const uint32_t slab_addr = smem_u32(slabs + slot * kTcSlabBytes);
+#pragma unroll
+                    for (uint32_t st = 0; st < kTcSlabSteps; st++)
+                        tc_mma_i8_ts(d_tmem, tmem + (g * kTcSlabSteps + st) * 8u, tc_smem_desc(slab_addr + 2u * st * kTcLbo),
+                                     kTcIdesc, (g | st) != 0u ? 1u : 0u);
+                    tc_commit(&s_slab_empty[slot]); // the slab may be overwritten once these MMAs have read it
+                }
+                tc_commit(&s_tmem_full[buf]);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 2) {
+        // ================= threshold publisher =================
+        // The floor of the histogram bucket where the count of candidates from the top reaches k is a
+        // lower bound of the query's k-th best score over everything the grid has scanned so far.
+        while (*reinterpret_cast<volatile unsigned int*>(&s_done) == 0) {
+            for (uint32_t j = blockIdx.x; j < nq; j += gridDim.x) {
+                const uint4* row = reinterpret_cast<const uint4*>(tp.ghist + (uint64_t) j * kSlicedHistBuckets) + lane * 8;
+                uint32_t c[32]; // this lane's 32 consecutive buckets
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const uint4 v = __ldcg(row + i);
+                    c[4 * i] = v.x, c[4 * i + 1] = v.y, c[4 * i + 2] = v.z, c[4 * i + 3] = v.w;
+                }
+                uint32_t mine = 0;
+#pragma unroll
+                for (int i = 0; i < 32; i++)
+                    mine += c[i];
+                uint32_t incl = mine; // candidates in this lane's buckets and above
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_down_sync(kFull, incl, d);
+                    if (lane + d < 32)
+                        incl += v;
+                }
+                const unsigned reach = __ballot_sync(kFull, incl >= p.k);
+                if (reach == 0)
+                    continue; // fewer than k candidates so far
+                if (lane == 31u - __clz(reach)) {
+                    uint32_t acc = incl - mine, bstar = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int i = 31; i >= 0; i--) {
+                        acc += c[i];
+                        if (!found && acc >= p.k) {
+                            found = true;
+                            bstar = lane * 32 + i;
+                        }
+                    }
+                    if (bstar >= 1) // candidates must beat tau strictly; the bucket floor itself stays eligible
+                        atomicMax(&tp.gtau[j], (static_cast<unsigned long long>(sliced_bucket_floor_bits(bstar)) << 32) - 1ull);
+                }
+            }
+            __nanosleep(2000);
+        }
+    } else if (warp >= kTcExpWarp0 && warp < kTcExpWarp0 + kTcExpWarps) {
+        // ================= expanders =================
+        const uint32_t e = warp - kTcExpWarp0;         // rows [16e, 16e+16) of the tile
+        const uint32_t batch = e >> 1, r_in_batch = (e & 1u) * 16u;
+        for (uint32_t n = 0; n < n_local; n++) {
+            const uint32_t t = blockIdx.x + n * gridDim.x, slot = n % kTcRawRing;
+            const uint32_t b0 = t * kTcTileBatches;
+            const uint32_t nb = p.n_batches - b0 < kTcTileBatches ? p.n_batches - b0 : kTcTileBatches;
+            TC_WAIT(&s_raw_full[slot], (n / kTcRawRing) & 1u);
+            const uint8_t* rb = raw + slot * kTcRawStage + batch * kTcRawBatch;
+            uint32_t w[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++)
+                w[i] = batch < nb ? reinterpret_cast<const uint32_t*>(rb)[(r_in_batch + i) * 32u + lane] : 0u;
+            if (lane < 16) {
+                const uint32_t pd = batch < nb ? reinterpret_cast<const uint16_t*>(rb + kBatchRows * 128u)[r_in_batch + lane] : 0u;
+                s_pdf[(n % kTcPdRing) * kTcTileRows + e * 16u + lane] = static_cast<float>(pd);
+            }
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&s_pd_full[n % kTcPdRing]);
+            for (uint32_t g = 0; g < kTcSlabs; g++) {
+                const uint32_t s = n * kTcSlabs + g, sslot = s % kTcSlabRing;
+                TC_WAIT(&s_slab_empty[sslot], ((s / kTcSlabRing) & 1u) ^ 1u);
+                uint8_t* dst = slabs + sslot * kTcSlabBytes + tc_slab_offset(e * 16u, lane);
+                const uint32_t m0 = 0x01010101u << (2u * g), m1 = m0 << 1;
+#pragma unroll
+                for (int i = 0; i < 16; i++) // row 16e+i: + (i >> 3) row groups, + (i & 7) rows
+                    *reinterpret_cast<uint2*>(dst + (i >> 3) * kTcSbo + (i & 7) * 16) = make_uint2(w[i] & m0, w[i] & m1);
+                fence_proxy_async_smem(); // the tensor core reads the slab through the async proxy
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(&s_slab_full[sslot]);
+                    if (g == 0)
+                        mbar_arrive(&s_raw_empty[slot]); // the raw rows are in registers
+                }
+            }
+        }
+    } else if (warp >= kTcEpiWarp0) {
+        // ================= epilogue =================
+        const uint32_t etid = tid - kTcEpiWarp0 * 32u;   // 0..255
+        const uint32_t half = ew >> 2;                    // columns [64 half, 64 half + 64)
+        const bool drop_zero = p.cutoff > 0.0f;
+        const bool live = qj < nq;
+        TcExact ex;
+        ex.p = &p;
+        ex.list = my_cand + (uint64_t) qj * kBatchListCap;
+        ex.tau = &s_tau[qj];
+        ex.surv = &s_surv[qj];
+        ex.cnt = &s_cnt[qj];
+        ex.need_select = &s_need_select;
+        ex.error = &s_error;
+        ex.ghist = tp.ghist + (uint64_t) qj * kSlicedHistBuckets;
+        ex.pq = pq;
+        ex.row_base32 = static_cast<uint32_t>(p.row_base);
+        ex.drop_zero = drop_zero;
+        unsigned long long tau_cached = 0;
+        float slope = 0.0f, thr = 0.0f;
+        // With a cutoff every row at or above it must be seen (survivor count), so the filter follows
+        // the cutoff; without one it follows the query's threshold.
+        auto refresh_filter = [&]() {
+            const float ts = drop_zero ? p.cutoff : __uint_as_float(static_cast<uint32_t>((tau_cached + 1ull) >> 32));
+            const float tq = sliced_tq(ts);
+            slope = tc_filter_slope(tq);
+            thr = live ? tc_filter_threshold(tq, pq) : __int_as_float(0x7f000000); // idle lanes never pass
+        };
+        refresh_filter();
+        for (uint32_t n = 0; n < n_local; n++) {
+            const uint32_t t = blockIdx.x + n * gridDim.x, buf = n & 1u;
+            ex.row0 = t * kTcTileRows;
+            const unsigned long long g_seen = (live && half == 0) ? __ldcg(&tp.gtau[qj]) : 0ull;
+            TC_WAIT(&s_pd_full[n % kTcPdRing], (n / kTcPdRing) & 1u);
+            TC_WAIT(&s_tmem_full[buf], (n >> 1) & 1u);
+            tc_fence_after();
+            const float* pdf = s_pdf + (n % kTcPdRing) * kTcTileRows + half * 64u;
+            const uint32_t taddr = tmem + ((quarter * 32u) << 16) + kTcTmemD + buf * kTcTileRows + half * 64u;
+            uint32_t v[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                tc_ld16(taddr + c * 16u, v[c]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0)
+                mbar_arrive(&s_tmem_empty[buf]); // the accumulators are in registers: the next-but-one tile may start
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                float pdv[16];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float4 f = *reinterpret_cast<const float4*>(pdf + c * 16 + i * 4);
+                    pdv[4 * i] = f.x, pdv[4 * i + 1] = f.y, pdv[4 * i + 2] = f.z, pdv[4 * i + 3] = f.w;
+                }
+                bool any = false;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    any |= __fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr;
+                if (any) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (__fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
+                            tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv[i]);
+                }
+            }
+            // ---- between tiles (the eight epilogue warps only): adopt the shared thresholds, cut lists back
+            const bool maint = n < 8 || (n & 3u) == 3u || *reinterpret_cast<volatile unsigned int*>(&s_need_select) != 0;
+            // (s_need_select is only read as a hint here; the decision below is taken after the barrier)
+            cta_sync<kTcEpiThreads>();
+            if (live && half == 0 && g_seen > s_tau[qj]) {
+                s_tau[qj] = g_seen;
+                s_flags[qj] |= kSlicedDirty;
+            }
+            cta_sync<kTcEpiThreads>();
+            (void) maint;
+            if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
+                batch_select_round<kTcEpiThreads>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, etid,
+                                                  [&](uint32_t j) { s_flags[j] |= kSlicedDirty; },
+                                                  [](uint32_t) { return false; });
+                if (etid == 0)
+                    s_need_select = 0;
+                cta_sync<kTcEpiThreads>();
+            }
+            // lists whose threshold rose drop the entries that fell below it (one warp per list)
+            for (uint32_t j = ew; j < nq; j += kTcEpiWarps) {
+                const uint32_t cnt = s_cnt[j];
+                if (!(s_flags[j] & kSlicedDirty))
+                    continue;
+                if (cnt > kTcPruneMin) {
+                    const unsigned long long tau = s_tau[j];
+                    unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
+                    uint32_t out = 0;
+                    for (uint32_t base = 0; base < cnt; base += 32) {
+                        const unsigned long long key = base + lane < cnt ? list[base + lane] : 0ull;
+                        __syncwarp();
+                        const bool keep = key > tau;
+                        const unsigned km = __ballot_sync(kFull, keep);
+                        if (keep)
+                            list[out + __popc(km & ((1u << lane) - 1u))] = key;
+                        out += __popc(km);
+                    }
+                    __syncwarp();
+                    if (lane == 0)
+                        s_cnt[j] = out;
+                }
+                __syncwarp();
+                if (lane == 0)
+                    s_flags[j] &= ~static_cast<unsigned int>(kSlicedDirty);
+            }
+            cta_sync<kTcEpiThreads>();
+            if (live) {
+                const unsigned long long tau_now = s_tau[qj];
+                if (tau_now != tau_cached) {
+                    tau_cached = tau_now;
+                    refresh_filter();
+                }
+            }
+        }
+        if (etid == 0)
+            *reinterpret_cast<volatile unsigned int*>(&s_done) = 1;
+        // ---- final per-CTA lists: short ones are sorted by one warp each, the rest by the eight warps together
+        cta_sync<kTcEpiThreads>();
+        for (uint32_t j = ew; j < nq; j += kTcEpiWarps) {
+            const uint32_t cnt = s_cnt[j];
+            if (cnt > kTcWarpSortMax)
+                continue;
+            sliced_warp_sort(my_cand + (uint64_t) j * kBatchListCap, cnt, p.k, lane);
+            if (lane == 0) {
+                s_cnt[j] = cnt < p.k ? cnt : p.k;
+                s_flags[j] |= kSlicedSorted;
+            }
+        }
+        cta_sync<kTcEpiThreads>();
+        batch_finish<kTcEpiThreads>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, etid,
+                                    [&](uint32_t j) { return (s_flags[j] & kSlicedSorted) != 0; });
+    }
+    // ---- teardown: every MMA has completed (the epilogue waited for all accumulator tiles)
+    tc_fence_before();
+    __syncthreads();
+#undef TC_WAIT
+    if (warp == 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTcTmemCols) : "memory");
+}
+
+} // namespace gsb

@@ -46,6 +46,7 @@ extern "C" {
 #define GSB_BATCH_LOOPED 0    /* one single-query scan per query                                      */
 #define GSB_BATCH_POPC 1      /* up to 256 queries per pass over the database (POPC kernel)           */
 #define GSB_BATCH_SLICED 2    /* up to 1024 queries per pass (bit-sliced kernel)                      */
+#define GSB_BATCH_TENSOR 3    /* 128 queries per pass on the tensor cores (tcgen05), 1024 per call    */
 
 /* *n of a device-side result when the launch failed without killing the context (a grid barrier
  * or peer flag timed out): the host-buffer entry points turn it into GSB_ERR_CUDA */
