@@ -33,7 +33,11 @@ tests/cpp/test_adapter: tests/cpp/test_adapter.cpp $(ADAPTER) oracle/qt_shims/gs
 tests/cpp/test_sliced_math: tests/cpp/test_sliced_math.cpp $(CSRC)/gsb_sliced_math.h
 	g++ -std=c++14 -O2 -Wall -Werror -o $@ tests/cpp/test_sliced_math.cpp
 
-adapter: $(ADAPTER) tests/cpp/test_adapter tests/cpp/test_sliced_math $(SERVER)
+# CPU emulation of the operands of the tensor-core multi-query kernel (layouts, dot products, filter)
+tests/cpp/test_tensor_math: tests/cpp/test_tensor_math.cpp $(CSRC)/gsb_tensor_math.h $(CSRC)/gsb_sliced_math.h
+	g++ -std=c++14 -O2 -Wall -Werror -o $@ tests/cpp/test_tensor_math.cpp
+
+adapter: $(ADAPTER) tests/cpp/test_adapter tests/cpp/test_sliced_math tests/cpp/test_tensor_math $(SERVER)
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_api.o $(CSRC)/gsb_api.cu

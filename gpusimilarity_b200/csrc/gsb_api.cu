@@ -1307,9 +1307,37 @@ int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
         tp.ghist = ws.shist + static_cast<size_t>(q0) * gsb::kSlicedHistBuckets;
         tp.gtau = ws.stau + q0;
         tp.n_tiles = n_tiles;
+        tp.fault = static_cast<uint32_t>(env_int("GSB_TC_FAULT", 0));
+        tp.variant = static_cast<uint32_t>(env_int("GSB_TC_VARIANT", 0));
+        unsigned long long* dbg = nullptr;
+        const size_t dbg_n = static_cast<size_t>(grid) * gsb::kTcWarps * 8;
+        if (env_int("GSB_TC_DEBUG", 0)) {
+            GSB_CUDA(cudaMalloc(&dbg, dbg_n * 8));
+            GSB_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * 8, st));
+        }
+        tp.dbg = dbg;
         void* args[] = {&tp};
         GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(gsb::kTcThreads), args, smem, st));
         g_launches++;
+        if (dbg) { // per-role wait times (clocks), averaged over the CTAs
+            std::vector<unsigned long long> h(dbg_n);
+            GSB_CUDA(cudaStreamSynchronize(st));
+            GSB_CUDA(cudaMemcpy(h.data(), dbg, dbg_n * 8, cudaMemcpyDeviceToHost));
+            cudaFree(dbg);
+            // (slots 0/1 double as phase timers: expanders = stores / fence, MMA = issue, epilogue = tmem loads / filter)
+            const char* site[8] = {"raw_empty|stores|issue|ldtm", "tmem_empty|fence|filter", "slab_full|epi arrive", "raw_full|mma fences", "slab_empty|commit", "pd_full|raw phase", "tmem_full", "role total"};
+            for (int w : {0, 1, 4, 11, 12, 19}) {
+                std::fprintf(stderr, "[gsb tc dbg] warp %2d:", w);
+                for (int i = 0; i < 8; i++) {
+                    double sum = 0;
+                    for (int c = 0; c < grid; c++)
+                        sum += static_cast<double>(h[(static_cast<size_t>(c) * gsb::kTcWarps + w) * 8 + i]);
+                    if (sum > 0)
+                        std::fprintf(stderr, " %s %.0f", site[i], sum / grid / std::max<uint32_t>(1, (n_tiles + grid - 1) / grid));
+                }
+                std::fprintf(stderr, "  (clocks per tile)\n");
+            }
+        }
     }
     return GSB_OK;
 }

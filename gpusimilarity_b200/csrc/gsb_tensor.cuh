@@ -46,7 +46,7 @@ constexpr uint32_t kTcPruneMin = 64, kTcWarpSortMax = 64;
 __host__ __device__ constexpr uint32_t tc_smem_bytes()
 {
     return kTcSlabRing * kTcSlabBytes + kTcRawRing * kTcRawStage + kBatchListCap * 8u + kBuckets * 4u +
-           kTcPdRing * kTcTileRows * 4u + kTcQueries * (8u + 8u + 4u + 4u);
+           kTcPdRing * kTcTileRows * 4u + kTcPdRing * 8u * 4u + kTcQueries * (8u + 8u + 4u + 4u);
 }
 
 struct TensorParams {
@@ -54,6 +54,9 @@ struct TensorParams {
     unsigned int* ghist;      // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
     unsigned long long* gtau; // [nq] thresholds shared by all CTAs; zero on entry
     uint32_t n_tiles;         // 128-row tiles of the shard
+    uint32_t fault;           // test hook (GSB_TC_FAULT=1): CTA 0 never loads its first tile -> pipeline timeout
+    uint32_t variant;         // GSB_TC_VARIANT: epilogue filter experiments (0 = two levels, 1 = one level)
+    unsigned long long* dbg;  // GSB_TC_DEBUG=1: [grid][20 warps][8] clocks spent in each pipeline wait, role time
 };
 
 // ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) --------------------------------------------------
@@ -110,24 +113,24 @@ constexpr uint32_t kTcIdesc = (2u << 4) | ((kTcTileRows >> 3) << 17) | ((kTcQuer
 
 // Pipeline wait with a way out: never hangs and never traps.  A wait that outlasts the launch's spin
 // bound raises kErrPipeline (reported like a grid-barrier timeout: every count becomes
-// GSB_COUNT_ERROR) and sets the abort flag, after which every wait of every role returns at once,
-// so the CTA runs to its end and the context stays usable.
-__device__ __forceinline__ void tc_wait(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
+// GSB_COUNT_ERROR) and sets the abort flag; every role leaves its loop at its next wait (false is
+// returned), touches no pipeline barrier again, and the CTA runs to its end: the context stays usable.
+__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
                                         unsigned int* error, unsigned long long timeout_ns)
 {
     if (mbar_try_wait(bar, parity))
-        return;
+        return true;
     const unsigned long long t0 = global_ns();
     for (uint32_t spins = 0;; spins++) {
         if (mbar_try_wait(bar, parity))
-            return;
+            return true;
         if ((spins & 63u) == 63u) {
             if (*abort_flag)
-                return;
+                return false;
             if (global_ns() - t0 > timeout_ns) {
                 atomicOr(error, kErrPipeline);
                 *abort_flag = 1;
-                return;
+                return false;
             }
         }
     }
@@ -181,20 +184,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     const BatchParams& p = tp.b;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t s_raw_full[kTcRawRing], s_raw_empty[kTcRawRing], s_slab_full[kTcSlabRing],
-        s_slab_empty[kTcSlabRing], s_tmem_full[2], s_tmem_empty[2], s_pd_full[kTcPdRing];
+        s_slab_empty[kTcSlabRing], s_tmem_full[2], s_tmem_empty[2], s_pd_full[kTcPdRing], s_drain;
     __shared__ uint32_t s_tmem_base;
     __shared__ unsigned long long s_stage_tau;
-    __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_need_select, s_error, s_done, s_abort;
+    __shared__ unsigned int s_stage_count, s_dummy_epoch, s_alive, s_need_select, s_error, s_done, s_abort, s_any_dirty;
 
-#define TC_WAIT(bar, parity) tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns)
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // site = which wait (0 raw_empty, 1 tmem_empty, 2 slab_full, 3 raw_full, 4 slab_empty, 5 pd_full, 6 tmem_full)
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool alive = true; // false once a pipeline wait of this thread gave up
+#define TC_WAIT(bar, parity, site)                                                               \
+    do {                                                                                         \
+        if (tp.dbg) {                                                                            \
+            const long long t_w = clock64();                                                     \
+            alive = tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns);                 \
+            dbg_acc[site] += clock64() - t_w;                                                    \
+        } else {                                                                                 \
+            alive = tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns);                 \
+        }                                                                                        \
+        if (warp >= kTcExpWarp0) /* whole warps wait there: one outcome for all lanes */         \
+            alive = __all_sync(0xffffffffu, alive);                                              \
+    } while (0)
     const uint32_t nq = p.nq;
     // shared memory carve-up
     uint8_t* slabs = smem;
     uint8_t* raw = slabs + kTcSlabRing * kTcSlabBytes;
     uint8_t* stage = raw + kTcRawRing * kTcRawStage;
     float* s_pdf = reinterpret_cast<float*>(stage + kBatchListCap * 8u + kBuckets * 4u); // [kTcPdRing][128]
-    unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_pdf + kTcPdRing * kTcTileRows); // [128]
+    float* s_pdmin = s_pdf + kTcPdRing * kTcTileRows;                                    // [kTcPdRing][8 chunks of 16 rows]
+    unsigned long long* s_tau = reinterpret_cast<unsigned long long*>(s_pdmin + kTcPdRing * 8u); // [128]
     unsigned long long* s_surv = s_tau + kTcQueries;
     unsigned int* s_cnt = reinterpret_cast<unsigned int*>(s_surv + kTcQueries);
     unsigned int* s_flags = s_cnt + kTcQueries;
@@ -233,12 +251,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         }
         for (uint32_t i = 0; i < kTcPdRing; i++)
             mbar_init(&s_pd_full[i], kTcExpWarps);
+        mbar_init(&s_drain, 1);
         mbar_fence_init();
         s_alive = 0;
         s_need_select = 0;
         s_error = 0;
         s_done = 0;
         s_abort = 0;
+        s_any_dirty = 0;
     }
     if (warp == 1) { // tensor memory: all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
@@ -283,15 +303,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     __syncthreads();
     tc_fence_after();
 
+    const long long dbg_t0 = tp.dbg ? clock64() : 0;
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            for (uint32_t n = 0; n < n_local; n++) {
+            for (uint32_t n = 0; n < n_local && alive; n++) {
                 const uint32_t t = blockIdx.x + n * gridDim.x, slot = n % kTcRawRing, use = n / kTcRawRing;
-                TC_WAIT(&s_raw_empty[slot], (use & 1u) ^ 1u);
+                TC_WAIT(&s_raw_empty[slot], (use & 1u) ^ 1u, 0);
+                if (!alive)
+                    break;
                 const uint32_t b0 = t * kTcTileBatches;
                 const uint32_t nb = p.n_batches - b0 < kTcTileBatches ? p.n_batches - b0 : kTcTileBatches;
                 mbar_arrive_expect_tx(&s_raw_full[slot], nb * kTcRawBatch);
+                if (tp.fault == 1 && blockIdx.x == 0 && n == 0)
+                    continue;
                 for (uint32_t b = 0; b < nb; b++)
                     tma_bulk_g2s(raw + slot * kTcRawStage + b * kTcRawBatch, p.tiles + (uint64_t)(b0 + b) * p.batch_stride,
                                  kTcRawBatch, &s_raw_full[slot]);
@@ -301,23 +326,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            for (uint32_t n = 0; n < n_local; n++) {
+            for (uint32_t n = 0; n < n_local && alive; n++) {
                 const uint32_t buf = n & 1u;
-                TC_WAIT(&s_tmem_empty[buf], ((n >> 1) & 1u) ^ 1u); // the epilogue has drained this accumulator tile
+                TC_WAIT(&s_tmem_empty[buf], ((n >> 1) & 1u) ^ 1u, 1); // the epilogue has drained this accumulator tile
+                if (!alive)
+                    break;
+                long long t_f = tp.dbg ? clock64() : 0;
                 tc_fence_after();
+                if (tp.dbg)
+                    dbg_acc[3] += clock64() - t_f;
                 const uint32_t d_tmem = tmem + kTcTmemD + buf * kTcTileRows;
                 for (uint32_t g = 0; g < kTcSlabs; g++) {
                     const uint32_t s = n * kTcSlabs + g, slot = s % kTcSlabRing;
-                    TC_WAIT(&s_slab_full[slot], (s / kTcSlabRing) & 1u);
+                    TC_WAIT(&s_slab_full[slot], (s / kTcSlabRing) & 1u, 2);
+                    if (!alive)
+                        break;
+                    t_f = tp.dbg ? clock64() : 0;
                     tc_fence_after();
+                    if (tp.dbg)
+                        dbg_acc[3] += clock64() - t_f;
                     const uint32_t slab_addr = smem_u32(slabs + slot * kTcSlabBytes);
+                    const long long t_a = tp.dbg ? clock64() : 0;
 #pragma unroll
                     for (uint32_t st = 0; st < kTcSlabSteps; st++)
                         tc_mma_i8_ts(d_tmem, tmem + (g * kTcSlabSteps + st) * 8u, tc_smem_desc(slab_addr + 2u * st * kTcLbo),
                                      kTcIdesc, (g | st) != 0u ? 1u : 0u);
                     tc_commit(&s_slab_empty[slot]); // the slab may be overwritten once these MMAs have read it
+                    if (tp.dbg)
+                        dbg_acc[0] += clock64() - t_a;
                 }
+                if (!alive)
+                    break;
+                t_f = tp.dbg ? clock64() : 0;
                 tc_commit(&s_tmem_full[buf]);
+                if (tp.dbg)
+                    dbg_acc[4] += clock64() - t_f;
+            }
+            if (!alive) { // gave up: let the MMAs in flight finish before tensor memory is released
+                tc_commit(&s_drain);
+                const unsigned long long t0 = global_ns();
+                while (!mbar_try_wait(&s_drain, 0) && global_ns() - t0 < p.spin_timeout_ns) {
+                }
             }
         }
         __syncwarp();
@@ -369,12 +418,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         // ================= expanders =================
         const uint32_t e = warp - kTcExpWarp0;         // rows [16e, 16e+16) of the tile
         const uint32_t batch = e >> 1, r_in_batch = (e & 1u) * 16u;
-        for (uint32_t n = 0; n < n_local; n++) {
+        for (uint32_t n = 0; n < n_local && alive; n++) {
             const uint32_t t = blockIdx.x + n * gridDim.x, slot = n % kTcRawRing;
             const uint32_t b0 = t * kTcTileBatches;
             const uint32_t nb = p.n_batches - b0 < kTcTileBatches ? p.n_batches - b0 : kTcTileBatches;
-            TC_WAIT(&s_raw_full[slot], (n / kTcRawRing) & 1u);
+            TC_WAIT(&s_raw_full[slot], (n / kTcRawRing) & 1u, 3);
+            if (!alive)
+                break;
             const uint8_t* rb = raw + slot * kTcRawStage + batch * kTcRawBatch;
+            const long long t_r = tp.dbg ? clock64() : 0;
             uint32_t w[16];
 #pragma unroll
             for (int i = 0; i < 16; i++)
@@ -382,20 +434,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             if (lane < 16) {
                 const uint32_t pd = batch < nb ? reinterpret_cast<const uint16_t*>(rb + kBatchRows * 128u)[r_in_batch + lane] : 0u;
                 s_pdf[(n % kTcPdRing) * kTcTileRows + e * 16u + lane] = static_cast<float>(pd);
+                const uint32_t pd_lo = __reduce_min_sync(0x0000ffffu, pd); // smallest popcount of this warp's 16 rows
+                if (lane == 0)
+                    s_pdmin[(n % kTcPdRing) * 8u + e] = static_cast<float>(pd_lo);
             }
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&s_pd_full[n % kTcPdRing]);
+            if (tp.dbg)
+                dbg_acc[5] += clock64() - t_r;
             for (uint32_t g = 0; g < kTcSlabs; g++) {
                 const uint32_t s = n * kTcSlabs + g, sslot = s % kTcSlabRing;
-                TC_WAIT(&s_slab_empty[sslot], ((s / kTcSlabRing) & 1u) ^ 1u);
+                TC_WAIT(&s_slab_empty[sslot], ((s / kTcSlabRing) & 1u) ^ 1u, 4);
+                if (!alive)
+                    break;
                 uint8_t* dst = slabs + sslot * kTcSlabBytes + tc_slab_offset(e * 16u, lane);
                 const uint32_t m0 = 0x01010101u << (2u * g), m1 = m0 << 1;
+                const long long t_a = tp.dbg ? clock64() : 0;
+                if (tp.fault != 2 && tp.fault != 4) { // (faults 2-4: timing experiments with void results)
 #pragma unroll
-                for (int i = 0; i < 16; i++) // row 16e+i: + (i >> 3) row groups, + (i & 7) rows
-                    *reinterpret_cast<uint2*>(dst + (i >> 3) * kTcSbo + (i & 7) * 16) = make_uint2(w[i] & m0, w[i] & m1);
-                fence_proxy_async_smem(); // the tensor core reads the slab through the async proxy
+                    for (int i = 0; i < 16; i++) // row 16e+i: + (i >> 3) row groups, + (i & 7) rows
+                        *reinterpret_cast<uint2*>(dst + (i >> 3) * kTcSbo + (i & 7) * 16) = make_uint2(w[i] & m0, w[i] & m1);
+                }
+                const long long t_b = tp.dbg ? clock64() : 0;
+                if (tp.fault != 2 && tp.fault != 4)
+                    fence_proxy_async_smem(); // the tensor core reads the slab through the async proxy
                 __syncwarp();
+                if (tp.dbg) {
+                    dbg_acc[0] += t_b - t_a;
+                    dbg_acc[1] += clock64() - t_b;
+                }
                 if (lane == 0) {
                     mbar_arrive(&s_slab_full[sslot]);
                     if (g == 0)
@@ -432,61 +500,112 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             thr = live ? tc_filter_threshold(tq, pq) : __int_as_float(0x7f000000); // idle lanes never pass
         };
         refresh_filter();
-        for (uint32_t n = 0; n < n_local; n++) {
+        for (uint32_t n = 0; n < n_local && alive; n++) {
             const uint32_t t = blockIdx.x + n * gridDim.x, buf = n & 1u;
             ex.row0 = t * kTcTileRows;
-            const unsigned long long g_seen = (live && half == 0) ? __ldcg(&tp.gtau[qj]) : 0ull;
-            TC_WAIT(&s_pd_full[n % kTcPdRing], (n / kTcPdRing) & 1u);
-            TC_WAIT(&s_tmem_full[buf], (n >> 1) & 1u);
+            const bool maint = n < 4 || (n & 3u) == 3u;
+            const unsigned long long g_seen = (maint && live && half == 0) ? __ldcg(&tp.gtau[qj]) : 0ull;
+            TC_WAIT(&s_pd_full[n % kTcPdRing], (n / kTcPdRing) & 1u, 5);
+            if (!alive)
+                break;
+            TC_WAIT(&s_tmem_full[buf], (n >> 1) & 1u, 6);
+            if (!alive)
+                break;
             tc_fence_after();
             const float* pdf = s_pdf + (n % kTcPdRing) * kTcTileRows + half * 64u;
             const uint32_t taddr = tmem + ((quarter * 32u) << 16) + kTcTmemD + buf * kTcTileRows + half * 64u;
             uint32_t v[4][16];
+            const long long t_a = tp.dbg ? clock64() : 0;
 #pragma unroll
             for (int c = 0; c < 4; c++)
                 tc_ld16(taddr + c * 16u, v[c]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const long long t_b = tp.dbg ? clock64() : 0;
             tc_fence_before();
             __syncwarp();
             if (lane == 0)
                 mbar_arrive(&s_tmem_empty[buf]); // the accumulators are in registers: the next-but-one tile may start
+            const long long t_c = tp.dbg ? clock64() : 0;
+            // (after a pipeline timeout the accumulators are meaningless: no candidates from them)
+            const bool aborted = *reinterpret_cast<volatile unsigned int*>(&s_abort) != 0 || tp.fault == 2 || tp.fault == 3;
+            // Level 1, no shared-memory traffic per value: every row of a 16-column chunk has at least
+            // pdmin set bits, so D can only pass the filter if D >= thr - 2^23 - slope * pdmin (slope <= 0);
+            // one integer max over the chunk and one compare.  Level 2 for the rare chunks that get
+            // through: the per-row test, then the exact path.
+            const float4 pm = *reinterpret_cast<const float4*>(s_pdmin + (n % kTcPdRing) * 8u + half * 4u);
+            const float pmin[4] = {pm.x, pm.y, pm.z, pm.w};
+            if (tp.variant == 1) { // one level: per-row popcounts for every value
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-                float pdv[16];
+                for (int c = 0; c < 4; c++) {
+                    if (aborted)
+                        break;
+                    float pdv[16];
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const float4 f = *reinterpret_cast<const float4*>(pdf + c * 16 + i * 4);
-                    pdv[4 * i] = f.x, pdv[4 * i + 1] = f.y, pdv[4 * i + 2] = f.z, pdv[4 * i + 3] = f.w;
-                }
-                bool any = false;
-#pragma unroll
-                for (int i = 0; i < 16; i++)
-                    any |= __fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr;
-                if (any) {
+                    for (int i = 0; i < 4; i++) {
+                        const float4 f = *reinterpret_cast<const float4*>(pdf + c * 16 + i * 4);
+                        pdv[4 * i] = f.x, pdv[4 * i + 1] = f.y, pdv[4 * i + 2] = f.z, pdv[4 * i + 3] = f.w;
+                    }
+                    bool any = false;
 #pragma unroll
                     for (int i = 0; i < 16; i++)
-                        if (__fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
-                            tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv[i]);
+                        any |= __fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr;
+                    if (any) {
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+                            if (__fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
+                                tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv[i]);
+                    }
+                }
+            } else
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                if (aborted)
+                    break;
+                const int32_t t1 = __float2int_rd(__fmaf_rn(-slope, pmin[c], thr - 8388608.0f)) - 1; // (saturates)
+                int32_t dmax = 0;
+#pragma unroll
+                for (int i = 0; i < 16; i++)
+                    dmax = max(dmax, static_cast<int32_t>(v[c][i]));
+                if (dmax >= t1) {
+#pragma unroll
+                    for (int i = 0; i < 16; i++)
+                        if (static_cast<int32_t>(v[c][i]) >= t1) {
+                            const float pdv = pdf[c * 16 + i];
+                            if (__fmaf_rn(slope, pdv, __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
+                                tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv);
+                        }
                 }
             }
-            // ---- between tiles (the eight epilogue warps only): adopt the shared thresholds, cut lists back
-            const bool maint = n < 8 || (n & 3u) == 3u || *reinterpret_cast<volatile unsigned int*>(&s_need_select) != 0;
-            // (s_need_select is only read as a hint here; the decision below is taken after the barrier)
-            cta_sync<kTcEpiThreads>();
+            const long long t_d = tp.dbg ? clock64() : 0;
+            if (tp.dbg) {
+                dbg_acc[0] += t_b - t_a;
+                dbg_acc[2] += t_c - t_b;
+                dbg_acc[1] += t_d - t_c;
+            }
+            // ---- every fourth tile (every tile during warm-up), the eight epilogue warps only: adopt
+            // the shared thresholds, cut lists back.  A list grows by at most 128 entries per tile and
+            // is cut once it is half full, so four tiles between two looks cannot overflow it.
+            if (!maint)
+                continue;
+            cta_sync<kTcEpiThreads>(); // every candidate of the tiles so far is in its list
             if (live && half == 0 && g_seen > s_tau[qj]) {
                 s_tau[qj] = g_seen;
                 s_flags[qj] |= kSlicedDirty;
+                *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = 1;
             }
             cta_sync<kTcEpiThreads>();
-            (void) maint;
             if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
                 batch_select_round<kTcEpiThreads>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, etid,
-                                                  [&](uint32_t j) { s_flags[j] |= kSlicedDirty; },
+                                                  [&](uint32_t) { // (the list was just cut and holds its new tau: no prune)
+                                                      *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = 1;
+                                                  },
                                                   [](uint32_t) { return false; });
                 if (etid == 0)
                     s_need_select = 0;
                 cta_sync<kTcEpiThreads>();
             }
+            if (*reinterpret_cast<volatile unsigned int*>(&s_any_dirty) == 0)
+                continue; // no threshold moved: nothing to prune, no filter to refresh
             // lists whose threshold rose drop the entries that fell below it (one warp per list)
             for (uint32_t j = ew; j < nq; j += kTcEpiWarps) {
                 const uint32_t cnt = s_cnt[j];
@@ -513,7 +632,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 if (lane == 0)
                     s_flags[j] &= ~static_cast<unsigned int>(kSlicedDirty);
             }
-            cta_sync<kTcEpiThreads>();
             if (live) {
                 const unsigned long long tau_now = s_tau[qj];
                 if (tau_now != tau_cached) {
@@ -521,6 +639,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     refresh_filter();
                 }
             }
+            cta_sync<kTcEpiThreads>(); // (everybody has seen the flag before it is cleared)
+            if (etid == 0)
+                s_any_dirty = 0;
         }
         if (etid == 0)
             *reinterpret_cast<volatile unsigned int*>(&s_done) = 1;
@@ -539,6 +660,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         cta_sync<kTcEpiThreads>();
         batch_finish<kTcEpiThreads>(p, cs, my_cand, s_cnt, s_tau, s_surv, &s_alive, etid,
                                     [&](uint32_t j) { return (s_flags[j] & kSlicedSorted) != 0; });
+    }
+    if (tp.dbg && lane == 0) {
+        dbg_acc[7] = clock64() - dbg_t0;
+        for (int i = 0; i < 8; i++)
+            tp.dbg[((uint64_t) blockIdx.x * kTcWarps + warp) * 8 + i] = static_cast<unsigned long long>(dbg_acc[i]);
     }
     // ---- teardown: every MMA has completed (the epilogue waited for all accumulator tiles)
     tc_fence_before();

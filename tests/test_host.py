@@ -137,3 +137,17 @@ def test_sliced_kernel_math_on_cpu():
     res = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_sliced_math")], capture_output=True, text=True,
                          timeout=300)
     assert res.returncode == 0 and "sliced math ok" in res.stdout, res.stdout + res.stderr
+
+
+def test_tensor_kernel_operands_on_cpu():
+    """tests/cpp/test_tensor_math.cpp: both operands of the tensor-core multi-query kernel built with
+    the kernel's own helpers (bit -> byte expansion with weights 2^plane / 2^(7-plane), slab and
+    tensor-memory layouts), read back the way tcgen05.mma reads the canonical K-major layout:
+    D = 128 * popc(q & d) for every pair; conflict-free stores; the epilogue filter never rejects a
+    pair the exact score comparison accepts."""
+    import subprocess
+    from conftest import ROOT
+    subprocess.run(["make", "-C", ROOT, "tests/cpp/test_tensor_math"], check=True, capture_output=True)
+    res = subprocess.run([os.path.join(ROOT, "tests", "cpp", "test_tensor_math")], capture_output=True, text=True,
+                         timeout=300)
+    assert res.returncode == 0 and "\nok (" in res.stdout, res.stdout + res.stderr
