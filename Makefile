@@ -7,8 +7,21 @@ LIB    := gpusimilarity_b200/libgpusim_b200.so
 
 all: $(LIB) adapter oracle
 
-$(LIB): $(CSRC)/gsb_api.cu $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/gsb_sliced.cuh $(CSRC)/gsb_sliced_math.h $(CSRC)/gsb_tensor.cuh $(CSRC)/gsb_tensor_math.h $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(CSRC)/gsb_api.cu $(CSRC)/fsim_reader.cpp $(CSRC)/gpusim_server.cpp -lz
+# Two CUDA translation units (they compile in parallel: make -j), host-only sources alongside.
+OBJ    := build/obj
+KHDRS  := $(CSRC)/gsb_kernels.cuh $(CSRC)/gsb_batch.cuh $(CSRC)/gsb_sliced.cuh $(CSRC)/gsb_sliced_math.h \
+          $(CSRC)/gsb_tensor_params.h $(CSRC)/gsb_tensor_math.h $(CSRC)/gsb_internal.h include/gpusim_b200.h
+$(OBJ)/gsb_api.o: $(CSRC)/gsb_api.cu $(KHDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/gsb_api.cu
+$(OBJ)/gsb_tensor.o: $(CSRC)/gsb_tensor.cu $(CSRC)/gsb_tensor.cuh $(KHDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $(CSRC)/gsb_tensor.cu
+$(OBJ)/%.o: $(CSRC)/%.cpp $(CSRC)/gsb_internal.h include/gpusim_b200.h
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(LIB): $(OBJ)/gsb_api.o $(OBJ)/gsb_tensor.o $(OBJ)/fsim_reader.o $(OBJ)/gpusim_server.o
+	$(NVCC) $(NVFLAGS) -shared -o $@ $^ -lz
 
 # gpusimserver without Qt: same command line as the reference's main.cpp (--cpu_only, --gpu_bitcount)
 SERVER := gpusimilarity_b200/gpusimserver_b200
@@ -41,11 +54,12 @@ adapter: $(ADAPTER) tests/cpp/test_adapter tests/cpp/test_sliced_math tests/cpp/
 
 ptxas-info:
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_api.o $(CSRC)/gsb_api.cu
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c -o /tmp/gsb_tensor.o $(CSRC)/gsb_tensor.cu
 
 oracle:
 	$(MAKE) -s -C oracle all
 
 clean:
-	rm -f $(LIB)
+	rm -rf $(LIB) $(OBJ)
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean ptxas-info adapter

@@ -256,6 +256,45 @@ def reference_cuda_leg(gsb, O, OC, np, sizes):
     return out
 
 
+# ------------------------------------------------------------------------------------ small shards
+def small_shard_leg(gsb, O, np, torch, ShardedSearcher, local_rank, sizes, peak_gbs):
+    """What BASELINE configs[1] (10 M rows) and one 8-way shard of configs[2] (125 M rows) cost per
+    query on one GPU, device-timed with the query resident: `stream_ms` = back to back on one stream
+    (programmatic dependent launch: the next scan starts while the last CTA still selects),
+    `latency_ms` = one query at a time with a synchronize in between.  The fixed cost per launch
+    (ramp + grid-wide select) is what the fraction of the copy peak loses on small shards."""
+    dev = torch.device("cuda", local_rank)
+    stream = torch.cuda.current_stream()
+    d_query = torch.from_numpy(O.synth_template(SEED, 32).copy()).to(dev)
+    out = []
+    for rows in sizes:
+        db = gsb.FingerprintDB.synthetic(rows, device=local_rank, seed=SEED, plant_period=PLANT_PERIOD)
+        s = ShardedSearcher(db, K, local_rank, None, 1)
+        for _ in range(10):
+            s.search_local(d_query.data_ptr(), CUTOFF, stream)
+        torch.cuda.synchronize()
+        reps = 100
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            s.search_local(d_query.data_ptr(), CUTOFF, stream)
+        b.record(stream); b.synchronize()
+        stream_ms = a.elapsed_time(b) / reps
+        lat = []
+        for _ in range(30):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); s.search_local(d_query.data_ptr(), CUTOFF, stream); b.record(stream); b.synchronize()
+            lat.append(a.elapsed_time(b))
+        gbs = rows * ROW_BYTES / (stream_ms * 1e-3) / 1e9
+        out.append({"rows": rows, "k": K, "stream_ms": stream_ms, "latency_ms": statistics.median(lat),
+                    "stream_gbs": gbs, "stream_frac_of_copy_peak": gbs / peak_gbs,
+                    "latency_gbs": rows * ROW_BYTES / (statistics.median(lat) * 1e-3) / 1e9})
+        del s
+        db.close()
+        log("small_shard", out[-1])
+    return out
+
+
 # ------------------------------------------------------------------------------------ multi-query leg
 def sm_clock_hz(clocks):
     mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
@@ -336,24 +375,45 @@ def multi_query_leg(gsb, O, np, torch, db, dist, world, rank, local_rank, rows_t
                                "list-entry fetches, filter and select are overhead, not algorithmic",
             "query_set_bits_total": set_bits, "traffic": None}
 
-    # ---- dense queries: cost is proportional to the set bits of the queries
+    # ---- dense queries: the bit-sliced kernel pays per set bit of the queries, the tensor-core kernel
+    # (tcgen05.mma kind::i8, 128 queries per launch) does not; both are timed on the same batches and
+    # must return identical keys.  GSB_BATCH_KERNEL forces the kernel for the device entry point (the
+    # host-buffer API picks by the batch's set-bit total).
     dense = []
     rng = np.random.default_rng(7)
+    keys_of = {}
+    mac_peak = 4.5e15 / 2   # dense i8 MAC/s (B200_PROFILING.md: 4.5 POPS = 2 ops per MAC)
     for bits in (32, 128, 512):
         dq_np = np.zeros((256, 32), dtype=np.uint32)
         for j in range(256):
             pos = rng.choice(1024, size=bits, replace=False)
             np.bitwise_or.at(dq_np[j], pos >> 5, np.uint32(1) << (pos & 31).astype(np.uint32))
         d_dq = torch.from_numpy(dq_np.view(np.int32)).to(dev)
+        entry = {"set_bits_per_query": bits, "queries": 256}
+        for mode, name in (("3", "sliced"), ("4", "tensor")):
+            os.environ["GSB_BATCH_KERNEL"] = mode
 
-        def run_dense():
-            s.search_device(d_dq.data_ptr(), 256, 0.0, stream)
-        run_dense()
-        torch.cuda.synchronize()
-        dms = timed(run_dense, reps=1)
-        dense.append({"set_bits_per_query": bits, "queries": 256, "batch_ms": dms,
-                      "row_query_per_s": rows_total * 256 / (dms * 1e-3),
-                      "lds_frac": (tiles_per_gpu * 256 * bits) / (dms * 1e-3) / peak})
+            def run_dense():
+                s.search_device(d_dq.data_ptr(), 256, 0.0, stream)
+            try:
+                run_dense()
+                torch.cuda.synchronize()
+                dms = timed(run_dense, reps=1)
+                keys_of[name] = (s.out_rows[:256 * k].clone(), s.out_scores[:256 * k].clone(), s.out_n[:256].clone())
+                entry[name + "_ms"] = dms
+                entry[name + "_row_query_per_s"] = rows_total * 256 / (dms * 1e-3)
+                if name == "sliced":
+                    entry["sliced_lds_frac"] = (tiles_per_gpu * 256 * bits) / (dms * 1e-3) / peak
+                else:
+                    entry["tensor_mac_frac"] = (rows_total / world) * 256 * 1024 / (dms * 1e-3) / mac_peak
+            except Exception as e:
+                entry[name + "_error"] = repr(e)
+        os.environ.pop("GSB_BATCH_KERNEL", None)
+        if "sliced" in keys_of and "tensor" in keys_of:
+            entry["identical_results"] = all(bool(torch.equal(a, b)) for a, b in zip(keys_of["sliced"], keys_of["tensor"]))
+        keys_of.clear()
+        dense.append(entry)
+        log("dense", entry)
     return {"workload": f"{rows_total} rows, {nq} queries per batch, top-{k}, {world} shard(s)",
             "batch_ms": ms, "queries_per_s": nq / (ms * 1e-3),
             "row_query_per_s": rows_total * nq / (ms * 1e-3), "queries_per_pass": group,
@@ -478,6 +538,7 @@ def main():
     ap.add_argument("--no-multi-query", action="store_true")
     ap.add_argument("--no-reference-cuda", action="store_true")
     ap.add_argument("--no-single-process", action="store_true")
+    ap.add_argument("--no-small-shard", action="store_true")
     ap.add_argument("--no-full-verify", action="store_true")
     ap.add_argument("--verify-budget-s", type=float, default=75.0)
     ap.add_argument("--verify-queries", type=int, default=32)
@@ -518,6 +579,14 @@ def main():
             reference_cuda = reference_cuda_leg(gsb, O, OC, np, sizes)
         except Exception as e:  # reporting only: never hide the headline number
             reference_cuda = [{"error": repr(e)}]
+
+    small_shard = None
+    if world == 1 and not args.no_small_shard and args.rows >= 100_000_000:
+        try:
+            small_shard = small_shard_leg(gsb, O, np, torch, ShardedSearcher, local_rank, [10_000_000, 125_000_000],
+                                          measured_peak_gbs()[0])
+        except Exception as e:
+            small_shard = [{"error": repr(e)}]
 
     # ---- the database: contiguous, equal shards of the synthetic rows, generated in HBM
     row_base, n_rows = shard_range(args.rows, rank, world)
@@ -734,6 +803,8 @@ def main():
             line["multi_query"] = multi_query
         if single_process is not None:
             line["single_process"] = single_process
+        if small_shard is not None:
+            line["small_shard"] = small_shard
         if reference_cuda is not None:
             line["reference_cuda"] = reference_cuda
             ing = [r["ingest"] for r in reference_cuda if isinstance(r, dict) and "ingest" in r]

@@ -8,7 +8,7 @@
 #include "gsb_batch.cuh"
 #include "gsb_kernels.cuh"
 #include "gsb_sliced.cuh"
-#include "gsb_tensor.cuh"
+#include "gsb_tensor_params.h"
 
 #include "../../include/gpusim_b200.h"
 #include "gsb_internal.h"
@@ -1294,8 +1294,6 @@ int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
     rc = gate_launch(sh.device, ws, st, grid);
     if (rc)
         return rc;
-    void* kernel = reinterpret_cast<void*>(gsb::scan_tensor_kernel);
-    GSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     GSB_CUDA(cudaMemsetAsync(ws.shist, 0, static_cast<size_t>(nq) * gsb::kSlicedHistBuckets * sizeof(unsigned int), st));
     GSB_CUDA(cudaMemsetAsync(ws.stau, 0, static_cast<size_t>(nq) * sizeof(unsigned long long), st));
     for (uint32_t q0 = 0; q0 < nq; q0 += gsb::kTcQueries) {
@@ -1316,8 +1314,7 @@ int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
             GSB_CUDA(cudaMemsetAsync(dbg, 0, dbg_n * 8, st));
         }
         tp.dbg = dbg;
-        void* args[] = {&tp};
-        GSB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(gsb::kTcThreads), args, smem, st));
+        GSB_CUDA(gsb::tensor_kernel_launch(tp, grid, st));
         g_launches++;
         if (dbg) { // per-role wait times (clocks), averaged over the CTAs
             std::vector<unsigned long long> h(dbg_n);
@@ -1325,7 +1322,7 @@ int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
             GSB_CUDA(cudaMemcpy(h.data(), dbg, dbg_n * 8, cudaMemcpyDeviceToHost));
             cudaFree(dbg);
             // (slots 0/1 double as phase timers: expanders = stores / fence, MMA = issue, epilogue = tmem loads / filter)
-            const char* site[8] = {"raw_empty|stores|issue|ldtm", "tmem_empty|fence|filter", "slab_full|epi arrive", "raw_full|mma fences", "slab_empty|commit", "pd_full|raw phase", "tmem_full", "role total"};
+            const char* site[8] = {"raw_empty|stores|issue|ldtm", "tmem_empty|fence|filter", "slab_full|epi arrive", "raw_full|mma fences", "slab_empty|commit|maint", "pd_full|raw phase", "tmem_full", "role total"};
             for (int w : {0, 1, 4, 11, 12, 19}) {
                 std::fprintf(stderr, "[gsb tc dbg] warp %2d:", w);
                 for (int i = 0; i < 8; i++) {
@@ -1333,7 +1330,7 @@ int tensor_launch_shard(const gsb_db* db, Shard& sh, cudaStream_t st, const uint
                     for (int c = 0; c < grid; c++)
                         sum += static_cast<double>(h[(static_cast<size_t>(c) * gsb::kTcWarps + w) * 8 + i]);
                     if (sum > 0)
-                        std::fprintf(stderr, " %s %.0f", site[i], sum / grid / std::max<uint32_t>(1, (n_tiles + grid - 1) / grid));
+                        std::fprintf(stderr, " %s %.2f", site[i], sum / grid / std::max<uint32_t>(1, (n_tiles + grid - 1) / grid));
                 }
                 std::fprintf(stderr, "  (clocks per tile)\n");
             }

@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_batch_kernel(const __grid_con
 
 // Merge of all-gathered per-rank batch records: one CTA per query.  Record layout per rank:
 // [nq][k] keys, then [nq] survivors, then [nq] counts (u64 each).
-__global__ void __launch_bounds__(kMergeThreads, 1)
+GSB_KERNEL void __launch_bounds__(kMergeThreads, 1)
 merge_batch_kernel(const unsigned long long* records, uint32_t n_ranks, uint32_t nq, uint32_t k, uint32_t cap,
                    uint32_t* out_rows, float* out_scores, uint32_t* out_n, unsigned long long* out_approx)
 {

@@ -106,7 +106,7 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t base, uint32_t off)
 }
 
 // Lists, popcounts and query blocks from the raw queries ([nq][words]): one thread per query.
-__global__ void __launch_bounds__(kMaxSlicedQueries, 1)
+GSB_KERNEL void __launch_bounds__(kMaxSlicedQueries, 1)
 sliced_build_lists_kernel(const uint32_t* __restrict__ queries, uint32_t nq, uint32_t words, uint16_t* lists,
                           uint32_t* lofs, uint16_t* ngrp, uint16_t* popq, SlicedMeta* meta)
 {

@@ -27,37 +27,10 @@
 // A launch takes up to 128 queries; larger batches are one launch per 128 queries.
 #pragma once
 
-#include "gsb_sliced.cuh"
-#include "gsb_tensor_math.h"
+#include "gsb_tensor_params.h"
 
 namespace gsb
 {
-
-constexpr uint32_t kTcSlabRing = 4;   // expanded slabs in flight (one tile)
-constexpr uint32_t kTcRawRing = 3;    // raw tiles in flight
-constexpr uint32_t kTcPdRing = 8;     // tiles whose row popcounts are kept: the expanders run up to 4 tiles ahead of the epilogue
-constexpr uint32_t kTcRawBatch = kBatchRows * 128u + kBatchRows * 2u; // 4160: 32 rows + u16 popcounts
-constexpr uint32_t kTcRawStage = kTcTileBatches * kTcRawBatch;        // 16640
-constexpr int kTcWarps = 20, kTcThreads = kTcWarps * 32;
-constexpr int kTcExpWarp0 = 4, kTcExpWarps = 8, kTcEpiWarp0 = 12, kTcEpiWarps = 8, kTcEpiThreads = kTcEpiWarps * 32;
-constexpr uint32_t kTcTmemCols = 512, kTcTmemD = 256; // columns [0,256): queries, [256,512): two accumulator tiles
-constexpr uint32_t kTcPruneMin = 64, kTcWarpSortMax = 64;
-
-__host__ __device__ constexpr uint32_t tc_smem_bytes()
-{
-    return kTcSlabRing * kTcSlabBytes + kTcRawRing * kTcRawStage + kBatchListCap * 8u + kBuckets * 4u +
-           kTcPdRing * kTcTileRows * 4u + kTcPdRing * 8u * 4u + kTcQueries * (8u + 8u + 4u + 4u);
-}
-
-struct TensorParams {
-    BatchParams b;            // database, k, cutoff, nq (<= 128), candidate lists, outputs
-    unsigned int* ghist;      // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
-    unsigned long long* gtau; // [nq] thresholds shared by all CTAs; zero on entry
-    uint32_t n_tiles;         // 128-row tiles of the shard
-    uint32_t fault;           // test hook (GSB_TC_FAULT=1): CTA 0 never loads its first tile -> pipeline timeout
-    uint32_t variant;         // GSB_TC_VARIANT: epilogue filter experiments (0 = two levels, 1 = one level)
-    unsigned long long* dbg;  // GSB_TC_DEBUG=1: [grid][20 warps][8] clocks spent in each pipeline wait, role time
-};
 
 // ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) --------------------------------------------------
 __device__ __forceinline__ void tc_fence_before()
@@ -99,6 +72,15 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16])
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ bool tc_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "elect.sync _|p, 0xffffffff;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(pred));
+    return pred != 0;
+}
 // Shared-memory matrix descriptor: K-major, no swizzle (core matrix = 8 rows x 16 bytes, contiguous),
 // leading byte offset = distance of the two 16-byte chunks of a K-step, stride byte offset =
 // distance of consecutive 8-row groups; bits 46-47 = descriptor version 1 (sm_100).
@@ -115,11 +97,11 @@ constexpr uint32_t kTcIdesc = (2u << 4) | ((kTcTileRows >> 3) << 17) | ((kTcQuer
 // bound raises kErrPipeline (reported like a grid-barrier timeout: every count becomes
 // GSB_COUNT_ERROR) and sets the abort flag; every role leaves its loop at its next wait (false is
 // returned), touches no pipeline barrier again, and the CTA runs to its end: the context stays usable.
-__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
-                                        unsigned int* error, unsigned long long timeout_ns)
+// (inlined at every wait: ptxas cannot give a function called from warpgroups with different setmaxnreg
+// limits one register allocation — C7600 —, and the loop is a dozen instructions)
+__device__ __forceinline__ bool tc_wait_slow(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
+                                         unsigned int* error, unsigned long long timeout_ns)
 {
-    if (mbar_try_wait(bar, parity))
-        return true;
     const unsigned long long t0 = global_ns();
     for (uint32_t spins = 0;; spins++) {
         if (mbar_try_wait(bar, parity))
@@ -135,6 +117,13 @@ __device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile
         }
     }
 }
+__device__ __forceinline__ bool tc_wait(uint64_t* bar, uint32_t parity, volatile unsigned int* abort_flag,
+                                        unsigned int* error, unsigned long long timeout_ns)
+{
+    if (mbar_try_wait(bar, parity))
+        return true;
+    return tc_wait_slow(bar, parity, abort_flag, error, timeout_ns);
+}
 
 // Everything the exact path of one (query, row) pair needs; lives in local memory, the path is rare.
 struct TcExact {
@@ -148,6 +137,7 @@ struct TcExact {
     unsigned int* ghist;            // the query's row of the grid-wide histogram
     uint32_t pq, row0, row_base32;  // query popcount, first row of the tile (shard numbering), shard base
     bool drop_zero;
+    bool hist_on;                   // count candidates in the grid-wide histogram (off for most CTAs' first tile)
 };
 
 __device__ __noinline__ void tc_exact(const TcExact& e, uint32_t d, uint32_t col, float pdf)
@@ -175,7 +165,24 @@ __device__ __noinline__ void tc_exact(const TcExact& e, uint32_t d, uint32_t col
         e.list[idx] = key;
     else
         atomicOr(e.error, kErrOverflow);
-    atomicAdd(&e.ghist[sliced_bucket(__float_as_uint(score))], 1u);
+    if (e.hist_on)
+        atomicAdd(&e.ghist[sliced_bucket(__float_as_uint(score))], 1u);
+}
+
+// Level 2 of the epilogue filter for one 16-column chunk that passed level 1: the per-row test,
+// then the exact path.  Out of line on purpose (see tc_wait).
+__device__ __noinline__ void tc_level2(const TcExact& e, float slope, float thr, const float* pdf, uint32_t col0,
+                                       uint32_t d0, uint32_t d1, uint32_t d2, uint32_t d3, uint32_t d4, uint32_t d5,
+                                       uint32_t d6, uint32_t d7, uint32_t d8, uint32_t d9, uint32_t d10, uint32_t d11,
+                                       uint32_t d12, uint32_t d13, uint32_t d14, uint32_t d15)
+{
+    const uint32_t d[16] = {d0, d1, d2, d3, d4, d5, d6, d7, d8, d9, d10, d11, d12, d13, d14, d15};
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const float pdv = pdf[i];
+        if (__fmaf_rn(slope, pdv, __uint_as_float(kTcMagicBits | d[i])) >= thr)
+            tc_exact(e, d[i], col0 + i, pdv);
+    }
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid_constant__ TensorParams tp)
@@ -195,14 +202,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     bool alive = true; // false once a pipeline wait of this thread gave up
 #define TC_WAIT(bar, parity, site)                                                               \
     do {                                                                                         \
-        if (tp.dbg) {                                                                            \
-            const long long t_w = clock64();                                                     \
-            alive = tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns);                 \
-            dbg_acc[site] += clock64() - t_w;                                                    \
+        if (tp.fault == 5 && (site) != 0 && (site) != 3) { /* timing experiment: free-running roles */ \
         } else {                                                                                 \
+            const long long t_w = tp.dbg ? clock64() : 0;                                        \
             alive = tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns);                 \
+            if (tp.dbg)                                                                          \
+                dbg_acc[site] += clock64() - t_w;                                                \
         }                                                                                        \
-        if (warp >= kTcExpWarp0) /* whole warps wait there: one outcome for all lanes */         \
+        if (warp >= kTcExpWarp0 || warp == 1) /* whole warps wait there: one outcome for all lanes */ \
             alive = __all_sync(0xffffffffu, alive);                                              \
     } while (0)
     const uint32_t nq = p.nq;
@@ -302,8 +309,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    // Registers follow the roles (per warpgroup of four warps): the epilogue keeps 64 accumulators and
+    // 32 row popcounts of its half tile in registers, everybody else needs few.
+    // 4 x 48 + 8 x 56 + 8 x 160 = 20 x 96, the kernel's own allocation.
+    // (each setmaxnreg sits at the head of its warpgroup's branch: that is how ptxas ties the new limit to the code)
 
     const long long dbg_t0 = tp.dbg ? clock64() : 0;
+    if (warp < kTcExpWarp0) {
+    //asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
@@ -325,51 +338,52 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         __syncwarp();
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            for (uint32_t n = 0; n < n_local && alive; n++) {
-                const uint32_t buf = n & 1u;
-                TC_WAIT(&s_tmem_empty[buf], ((n >> 1) & 1u) ^ 1u, 1); // the epilogue has drained this accumulator tile
+        // The whole warp walks the loop (every address is warp-uniform: uniform registers, no
+        // per-lane waterfall around the tensor-core instructions); one elected lane issues.
+        const bool leader = tc_elect_one();
+        const uint32_t tmem_u = __shfl_sync(kFull, tmem, 0);
+        const uint32_t slabs_u = __shfl_sync(kFull, smem_u32(slabs), 0);
+        for (uint32_t n = 0; n < n_local && alive; n++) {
+            const uint32_t buf = n & 1u;
+            TC_WAIT(&s_tmem_empty[buf], ((n >> 1) & 1u) ^ 1u, 1); // the epilogue has drained this accumulator tile
+            if (!alive)
+                break;
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_u + kTcTmemD + buf * kTcTileRows;
+            for (uint32_t g = 0; g < kTcSlabs; g++) {
+                const uint32_t s = n * kTcSlabs + g, slot = s % kTcSlabRing;
+                TC_WAIT(&s_slab_full[slot], (s / kTcSlabRing) & 1u, 2);
                 if (!alive)
                     break;
-                long long t_f = tp.dbg ? clock64() : 0;
                 tc_fence_after();
-                if (tp.dbg)
-                    dbg_acc[3] += clock64() - t_f;
-                const uint32_t d_tmem = tmem + kTcTmemD + buf * kTcTileRows;
-                for (uint32_t g = 0; g < kTcSlabs; g++) {
-                    const uint32_t s = n * kTcSlabs + g, slot = s % kTcSlabRing;
-                    TC_WAIT(&s_slab_full[slot], (s / kTcSlabRing) & 1u, 2);
-                    if (!alive)
-                        break;
-                    t_f = tp.dbg ? clock64() : 0;
-                    tc_fence_after();
-                    if (tp.dbg)
-                        dbg_acc[3] += clock64() - t_f;
-                    const uint32_t slab_addr = smem_u32(slabs + slot * kTcSlabBytes);
-                    const long long t_a = tp.dbg ? clock64() : 0;
+                const uint32_t slab_addr = slabs_u + slot * kTcSlabBytes;
+                const long long t_a = tp.dbg ? clock64() : 0;
+                if (leader) {
 #pragma unroll
                     for (uint32_t st = 0; st < kTcSlabSteps; st++)
-                        tc_mma_i8_ts(d_tmem, tmem + (g * kTcSlabSteps + st) * 8u, tc_smem_desc(slab_addr + 2u * st * kTcLbo),
+                        tc_mma_i8_ts(d_tmem, tmem_u + (g * kTcSlabSteps + st) * 8u, tc_smem_desc(slab_addr + 2u * st * kTcLbo),
                                      kTcIdesc, (g | st) != 0u ? 1u : 0u);
                     tc_commit(&s_slab_empty[slot]); // the slab may be overwritten once these MMAs have read it
-                    if (tp.dbg)
-                        dbg_acc[0] += clock64() - t_a;
                 }
-                if (!alive)
-                    break;
-                t_f = tp.dbg ? clock64() : 0;
-                tc_commit(&s_tmem_full[buf]);
+                __syncwarp();
                 if (tp.dbg)
-                    dbg_acc[4] += clock64() - t_f;
+                    dbg_acc[0] += clock64() - t_a;
             }
-            if (!alive) { // gave up: let the MMAs in flight finish before tensor memory is released
+            if (!alive)
+                break;
+            if (leader)
+                tc_commit(&s_tmem_full[buf]);
+            __syncwarp();
+        }
+        if (!alive || tp.fault == 5) { // gave up: let the MMAs in flight finish before tensor memory is released
+            if (leader) {
                 tc_commit(&s_drain);
                 const unsigned long long t0 = global_ns();
                 while (!mbar_try_wait(&s_drain, 0) && global_ns() - t0 < p.spin_timeout_ns) {
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else if (warp == 2) {
         // ================= threshold publisher =================
         // The floor of the histogram bucket where the count of candidates from the top reaches k is a
@@ -414,7 +428,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             }
             __nanosleep(2000);
         }
-    } else if (warp >= kTcExpWarp0 && warp < kTcExpWarp0 + kTcExpWarps) {
+    }
+    } else if (warp < kTcEpiWarp0) {
+        //asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         // ================= expanders =================
         const uint32_t e = warp - kTcExpWarp0;         // rows [16e, 16e+16) of the tile
         const uint32_t batch = e >> 1, r_in_batch = (e & 1u) * 16u;
@@ -434,9 +450,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             if (lane < 16) {
                 const uint32_t pd = batch < nb ? reinterpret_cast<const uint16_t*>(rb + kBatchRows * 128u)[r_in_batch + lane] : 0u;
                 s_pdf[(n % kTcPdRing) * kTcTileRows + e * 16u + lane] = static_cast<float>(pd);
-                const uint32_t pd_lo = __reduce_min_sync(0x0000ffffu, pd); // smallest popcount of this warp's 16 rows
-                if (lane == 0)
-                    s_pdmin[(n % kTcPdRing) * 8u + e] = static_cast<float>(pd_lo);
             }
             __syncwarp();
             if (lane == 0)
@@ -471,7 +484,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 }
             }
         }
-    } else if (warp >= kTcEpiWarp0) {
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
         // ================= epilogue =================
         const uint32_t etid = tid - kTcEpiWarp0 * 32u;   // 0..255
         const uint32_t half = ew >> 2;                    // columns [64 half, 64 half + 64)
@@ -503,16 +517,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         for (uint32_t n = 0; n < n_local && alive; n++) {
             const uint32_t t = blockIdx.x + n * gridDim.x, buf = n & 1u;
             ex.row0 = t * kTcTileRows;
+            // Every value of a CTA's first tile is a candidate (threshold 0).  The first thresholds need
+            // k of them per query, not 128 per CTA: only the first 16 CTAs count theirs, the other
+            // 130 x 128 x nq same-address atomics on a few histogram buckets are skipped.
+            ex.hist_on = n != 0 || blockIdx.x < kTcWarmCtas || tp.variant == 1;
             const bool maint = n < 4 || (n & 3u) == 3u;
             const unsigned long long g_seen = (maint && live && half == 0) ? __ldcg(&tp.gtau[qj]) : 0ull;
             TC_WAIT(&s_pd_full[n % kTcPdRing], (n / kTcPdRing) & 1u, 5);
             if (!alive)
                 break;
+            // the row popcounts of this half tile: 16 broadcast loads, in flight while the tile is computed
+            const float* pdf = s_pdf + (n % kTcPdRing) * kTcTileRows + half * 64u;
+            float4 pnext[4]; // (chunk c + 1 is loaded while chunk c is tested)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                pnext[i] = *reinterpret_cast<const float4*>(pdf + i * 4);
             TC_WAIT(&s_tmem_full[buf], (n >> 1) & 1u, 6);
             if (!alive)
                 break;
             tc_fence_after();
-            const float* pdf = s_pdf + (n % kTcPdRing) * kTcTileRows + half * 64u;
             const uint32_t taddr = tmem + ((quarter * 32u) << 16) + kTcTmemD + buf * kTcTileRows + half * 64u;
             uint32_t v[4][16];
             const long long t_a = tp.dbg ? clock64() : 0;
@@ -527,53 +550,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 mbar_arrive(&s_tmem_empty[buf]); // the accumulators are in registers: the next-but-one tile may start
             const long long t_c = tp.dbg ? clock64() : 0;
             // (after a pipeline timeout the accumulators are meaningless: no candidates from them)
-            const bool aborted = *reinterpret_cast<volatile unsigned int*>(&s_abort) != 0 || tp.fault == 2 || tp.fault == 3;
-            // Level 1, no shared-memory traffic per value: every row of a 16-column chunk has at least
-            // pdmin set bits, so D can only pass the filter if D >= thr - 2^23 - slope * pdmin (slope <= 0);
-            // one integer max over the chunk and one compare.  Level 2 for the rare chunks that get
-            // through: the per-row test, then the exact path.
-            const float4 pm = *reinterpret_cast<const float4*>(s_pdmin + (n % kTcPdRing) * 8u + half * 4u);
-            const float pmin[4] = {pm.x, pm.y, pm.z, pm.w};
-            if (tp.variant == 1) { // one level: per-row popcounts for every value
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    if (aborted)
-                        break;
-                    float pdv[16];
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const float4 f = *reinterpret_cast<const float4*>(pdf + c * 16 + i * 4);
-                        pdv[4 * i] = f.x, pdv[4 * i + 1] = f.y, pdv[4 * i + 2] = f.z, pdv[4 * i + 3] = f.w;
-                    }
-                    bool any = false;
-#pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        any |= __fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr;
-                    if (any) {
-#pragma unroll
-                        for (int i = 0; i < 16; i++)
-                            if (__fmaf_rn(slope, pdv[i], __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
-                                tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv[i]);
-                    }
-                }
-            } else
+            const bool aborted = *reinterpret_cast<volatile unsigned int*>(&s_abort) != 0 || tp.fault == 2 || tp.fault == 3 || tp.fault == 5;
+            // Level 1: the per-row test itself, folded into one running maximum per 16-column chunk
+            // (per value: OR of the magic exponent, FMA with the row's popcount, FMNMX; no memory
+            // operation), one compare per chunk.  Level 2 (out of line) only for the
+            // chunks in which some row can really beat the query's threshold: it finds the row and
+            // takes the exact path.
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 if (aborted)
                     break;
-                const int32_t t1 = __float2int_rd(__fmaf_rn(-slope, pmin[c], thr - 8388608.0f)) - 1; // (saturates)
-                int32_t dmax = 0;
+                float m = -3.0e38f;
+                float4 pcur[4];
 #pragma unroll
-                for (int i = 0; i < 16; i++)
-                    dmax = max(dmax, static_cast<int32_t>(v[c][i]));
-                if (dmax >= t1) {
+                for (int i = 0; i < 4; i++) {
+                    pcur[i] = pnext[i];
+                    if (c < 3)
+                        pnext[i] = *reinterpret_cast<const float4*>(pdf + (c + 1) * 16 + i * 4);
+                }
 #pragma unroll
-                    for (int i = 0; i < 16; i++)
-                        if (static_cast<int32_t>(v[c][i]) >= t1) {
-                            const float pdv = pdf[c * 16 + i];
-                            if (__fmaf_rn(slope, pdv, __uint_as_float(kTcMagicBits | v[c][i])) >= thr)
-                                tc_exact(ex, v[c][i], half * 64u + c * 16u + i, pdv);
-                        }
+                for (int i = 0; i < 4; i++) {
+                    const float4 f = pcur[i];
+                    m = fmaxf(m, __fmaf_rn(slope, f.x, __uint_as_float(kTcMagicBits | v[c][4 * i])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.y, __uint_as_float(kTcMagicBits | v[c][4 * i + 1])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.z, __uint_as_float(kTcMagicBits | v[c][4 * i + 2])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.w, __uint_as_float(kTcMagicBits | v[c][4 * i + 3])));
+                }
+                if (m >= thr && tp.fault != 6) { // rare: a call, so that the hot loop stays a few hundred instructions
+                    if (tp.dbg)
+                        dbg_acc[3]++; // (GSB_TC_DEBUG: chunks of lane 0's query that pass level 1)
+                    tc_level2(ex, slope, thr, pdf + c * 16, half * 64u + c * 16u, v[c][0], v[c][1], v[c][2], v[c][3],
+                              v[c][4], v[c][5], v[c][6], v[c][7], v[c][8], v[c][9], v[c][10], v[c][11], v[c][12], v[c][13],
+                              v[c][14], v[c][15]);
                 }
             }
             const long long t_d = tp.dbg ? clock64() : 0;
@@ -587,13 +595,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             // is cut once it is half full, so four tiles between two looks cannot overflow it.
             if (!maint)
                 continue;
-            cta_sync<kTcEpiThreads>(); // every candidate of the tiles so far is in its list
-            if (live && half == 0 && g_seen > s_tau[qj]) {
+            const long long t_m = tp.dbg ? clock64() : 0;
+            auto maint_done = [&]() {
+                if (tp.dbg)
+                    dbg_acc[4] += clock64() - t_m; // (GSB_TC_DEBUG: epilogue slot 4 = maintenance)
+            };
+            // thread (half 0, lane) owns query qj: adopt the grid-wide threshold if it rose
+            const bool adopted = live && half == 0 && g_seen > s_tau[qj];
+            if (adopted)
                 s_tau[qj] = g_seen;
-                s_flags[qj] |= kSlicedDirty;
+            unsigned dirty_mask = __ballot_sync(kFull, adopted); // (queries 32 quarter + bit; half-0 warps)
+            if (dirty_mask && lane == 0)
                 *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = 1;
-            }
-            cta_sync<kTcEpiThreads>();
+            cta_sync<kTcEpiThreads>(); // every candidate of the tiles so far is in its list, every new threshold in s_tau
             if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
                 batch_select_round<kTcEpiThreads>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, etid,
                                                   [&](uint32_t) { // (the list was just cut and holds its new tau: no prune)
@@ -604,13 +618,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     s_need_select = 0;
                 cta_sync<kTcEpiThreads>();
             }
-            if (*reinterpret_cast<volatile unsigned int*>(&s_any_dirty) == 0)
+            if (*reinterpret_cast<volatile unsigned int*>(&s_any_dirty) == 0) {
+                maint_done();
                 continue; // no threshold moved: nothing to prune, no filter to refresh
-            // lists whose threshold rose drop the entries that fell below it (one warp per list)
-            for (uint32_t j = ew; j < nq; j += kTcEpiWarps) {
+            }
+            // lists whose threshold rose drop the entries that fell below it (the warp that owns the query)
+            while (dirty_mask) {
+                const uint32_t j = quarter * 32u + (__ffs(dirty_mask) - 1u);
+                dirty_mask &= dirty_mask - 1u;
                 const uint32_t cnt = s_cnt[j];
-                if (!(s_flags[j] & kSlicedDirty))
-                    continue;
                 if (cnt > kTcPruneMin) {
                     const unsigned long long tau = s_tau[j];
                     unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
@@ -629,8 +645,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                         s_cnt[j] = out;
                 }
                 __syncwarp();
-                if (lane == 0)
-                    s_flags[j] &= ~static_cast<unsigned int>(kSlicedDirty);
             }
             if (live) {
                 const unsigned long long tau_now = s_tau[qj];
@@ -639,9 +653,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     refresh_filter();
                 }
             }
-            cta_sync<kTcEpiThreads>(); // (everybody has seen the flag before it is cleared)
+            cta_sync<kTcEpiThreads>(); // (everybody has seen the flag before it is cleared; pruned counts are final)
             if (etid == 0)
                 s_any_dirty = 0;
+            maint_done();
         }
         if (etid == 0)
             *reinterpret_cast<volatile unsigned int*>(&s_done) = 1;
