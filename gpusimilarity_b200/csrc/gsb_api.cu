@@ -993,9 +993,10 @@ int scan_topk(const gsb_db* db, const uint32_t* q_dev_words, uint64_t k_total, f
 enum BatchKernel { kBatchNone = 0, kBatchPopc = 1, kBatchSliced = 2, kBatchTensor = 3 };
 
 // Cost model of the automatic choice between the bit-sliced and the tensor-core kernel, in
-// milliseconds per 10^9 rows on one B200 (profiles/r02_tensor.md): the bit-sliced kernel pays per
-// set bit of the batch, the tensor-core kernel per group of 128 queries.
-constexpr double kSlicedMsBase = 50.0, kSlicedMsPerSetBit = 7.6e-3, kTensorMsPerGroup = 80.0;
+// milliseconds per 10^9 rows on one B200 (profiles/r02_tensor.md: fits of the dense-query sweep): the
+// bit-sliced kernel pays per set bit of the batch, the tensor-core kernel per group of 128 queries;
+// they meet at ~140 set bits per query.
+constexpr double kSlicedMsBase = 47.0, kSlicedMsPerSetBit = 7.9e-3, kTensorMsPerGroup = 164.0;
 
 // set_bits: set bits of all queries of the batch together (-1 = not known: queries in device memory)
 BatchKernel batch_kernel_choice(const gsb_db* db, uint32_t k, int n_queries, float cutoff, int64_t set_bits = -1)

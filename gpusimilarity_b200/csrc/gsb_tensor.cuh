@@ -32,6 +32,17 @@
 namespace gsb
 {
 
+// setmaxnreg per warpgroup (48 / 56 / 160) compiles and its toy form runs (tools/probe/setmaxnreg_probe.cu),
+// but this kernel hangs with it on the B200 (first launch never returns); off until that is understood.
+#ifndef GSB_TC_SETMAXNREG
+#define GSB_TC_SETMAXNREG 0
+#endif
+#if GSB_TC_SETMAXNREG
+#define TC_SETMAXNREG(what) asm volatile("setmaxnreg." what ";")
+#else
+#define TC_SETMAXNREG(what) do { } while (0)
+#endif
+
 // ---- tcgen05 wrappers (PTX ISA 8.6+, sm_100a) --------------------------------------------------
 __device__ __forceinline__ void tc_fence_before()
 {
@@ -309,14 +320,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // Registers follow the roles (per warpgroup of four warps): the epilogue keeps 64 accumulators and
-    // 32 row popcounts of its half tile in registers, everybody else needs few.
-    // 4 x 48 + 8 x 56 + 8 x 160 = 20 x 96, the kernel's own allocation.
+    // (GSB_TC_SETMAXNREG: registers follow the roles per warpgroup, 4 x 48 + 8 x 56 + 8 x 160 = 20 x 96)
     // (each setmaxnreg sits at the head of its warpgroup's branch: that is how ptxas ties the new limit to the code)
 
     const long long dbg_t0 = tp.dbg ? clock64() : 0;
     if (warp < kTcExpWarp0) {
-    //asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+    //TC_SETMAXNREG("dec.sync.aligned.u32 48");
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         }
     }
     } else if (warp < kTcEpiWarp0) {
-        //asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        //TC_SETMAXNREG("dec.sync.aligned.u32 56");
         // ================= expanders =================
         const uint32_t e = warp - kTcExpWarp0;         // rows [16e, 16e+16) of the tile
         const uint32_t batch = e >> 1, r_in_batch = (e & 1u) * 16u;
@@ -485,7 +494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+        TC_SETMAXNREG("inc.sync.aligned.u32 160");
         // ================= epilogue =================
         const uint32_t etid = tid - kTcEpiWarp0 * 32u;   // 0..255
         const uint32_t half = ew >> 2;                    // columns [64 half, 64 half + 64)
@@ -537,30 +546,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 break;
             tc_fence_after();
             const uint32_t taddr = tmem + ((quarter * 32u) << 16) + kTcTmemD + buf * kTcTileRows + half * 64u;
-            uint32_t v[4][16];
+            // The half tile comes out of tensor memory 16 columns at a time, the next chunk (and its
+            // row popcounts) in flight while the current one is tested: 32 + 32 registers instead of
+            // 64 + 64, which keeps the loop free of spills at 96 registers per thread.
+            uint32_t v[2][16];
             const long long t_a = tp.dbg ? clock64() : 0;
-#pragma unroll
-            for (int c = 0; c < 4; c++)
-                tc_ld16(taddr + c * 16u, v[c]);
+            tc_ld16(taddr, v[0]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const long long t_b = tp.dbg ? clock64() : 0;
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0)
-                mbar_arrive(&s_tmem_empty[buf]); // the accumulators are in registers: the next-but-one tile may start
-            const long long t_c = tp.dbg ? clock64() : 0;
             // (after a pipeline timeout the accumulators are meaningless: no candidates from them)
             const bool aborted = *reinterpret_cast<volatile unsigned int*>(&s_abort) != 0 || tp.fault == 2 || tp.fault == 3 || tp.fault == 5;
             // Level 1: the per-row test itself, folded into one running maximum per 16-column chunk
             // (per value: OR of the magic exponent, FMA with the row's popcount, FMNMX; no memory
-            // operation), one compare per chunk.  Level 2 (out of line) only for the
-            // chunks in which some row can really beat the query's threshold: it finds the row and
-            // takes the exact path.
+            // operation on the dependent path), one compare per chunk.  Level 2 (out of line) only
+            // for the chunks in which some row can really beat the query's threshold: it finds the
+            // row and takes the exact path.
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                if (aborted)
-                    break;
-                float m = -3.0e38f;
                 float4 pcur[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -568,28 +569,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     if (c < 3)
                         pnext[i] = *reinterpret_cast<const float4*>(pdf + (c + 1) * 16 + i * 4);
                 }
+                if (c < 3)
+                    tc_ld16(taddr + (c + 1) * 16u, v[(c + 1) & 1]);
+                float m = -3.0e38f;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float4 f = pcur[i];
-                    m = fmaxf(m, __fmaf_rn(slope, f.x, __uint_as_float(kTcMagicBits | v[c][4 * i])));
-                    m = fmaxf(m, __fmaf_rn(slope, f.y, __uint_as_float(kTcMagicBits | v[c][4 * i + 1])));
-                    m = fmaxf(m, __fmaf_rn(slope, f.z, __uint_as_float(kTcMagicBits | v[c][4 * i + 2])));
-                    m = fmaxf(m, __fmaf_rn(slope, f.w, __uint_as_float(kTcMagicBits | v[c][4 * i + 3])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.x, __uint_as_float(kTcMagicBits | v[c & 1][4 * i])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.y, __uint_as_float(kTcMagicBits | v[c & 1][4 * i + 1])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.z, __uint_as_float(kTcMagicBits | v[c & 1][4 * i + 2])));
+                    m = fmaxf(m, __fmaf_rn(slope, f.w, __uint_as_float(kTcMagicBits | v[c & 1][4 * i + 3])));
                 }
-                if (m >= thr && tp.fault != 6) { // rare: a call, so that the hot loop stays a few hundred instructions
+                if (m >= thr && !aborted && tp.fault != 6) { // rare: a call, so that the hot loop stays small
                     if (tp.dbg)
                         dbg_acc[3]++; // (GSB_TC_DEBUG: chunks of lane 0's query that pass level 1)
-                    tc_level2(ex, slope, thr, pdf + c * 16, half * 64u + c * 16u, v[c][0], v[c][1], v[c][2], v[c][3],
-                              v[c][4], v[c][5], v[c][6], v[c][7], v[c][8], v[c][9], v[c][10], v[c][11], v[c][12], v[c][13],
-                              v[c][14], v[c][15]);
+                    tc_level2(ex, slope, thr, pdf + c * 16, half * 64u + c * 16u, v[c & 1][0], v[c & 1][1], v[c & 1][2],
+                              v[c & 1][3], v[c & 1][4], v[c & 1][5], v[c & 1][6], v[c & 1][7], v[c & 1][8], v[c & 1][9],
+                              v[c & 1][10], v[c & 1][11], v[c & 1][12], v[c & 1][13], v[c & 1][14], v[c & 1][15]);
+                }
+                if (c < 3)
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c == 2) { // the last chunk is in registers: the next-but-one tile may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0)
+                        mbar_arrive(&s_tmem_empty[buf]);
                 }
             }
-            const long long t_d = tp.dbg ? clock64() : 0;
-            if (tp.dbg) {
-                dbg_acc[0] += t_b - t_a;
-                dbg_acc[2] += t_c - t_b;
-                dbg_acc[1] += t_d - t_c;
-            }
+            if (tp.dbg)
+                dbg_acc[1] += clock64() - t_a; // (GSB_TC_DEBUG: epilogue slot 1 = tensor-memory loads + filter)
             // ---- every fourth tile (every tile during warm-up), the eight epilogue warps only: adopt
             // the shared thresholds, cut lists back.  A list grows by at most 128 entries per tile and
             // is cut once it is half full, so four tiles between two looks cannot overflow it.
@@ -606,19 +614,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 s_tau[qj] = g_seen;
             unsigned dirty_mask = __ballot_sync(kFull, adopted); // (queries 32 quarter + bit; half-0 warps)
             if (dirty_mask && lane == 0)
-                *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = 1;
+                *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = n + 1u; // (a stamp, never cleared)
             cta_sync<kTcEpiThreads>(); // every candidate of the tiles so far is in its list, every new threshold in s_tau
             if (*reinterpret_cast<volatile unsigned int*>(&s_need_select)) {
                 batch_select_round<kTcEpiThreads>(cs, my_cand, s_cnt, s_tau, nq, p.k, false, etid,
                                                   [&](uint32_t) { // (the list was just cut and holds its new tau: no prune)
-                                                      *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = 1;
+                                                      *reinterpret_cast<volatile unsigned int*>(&s_any_dirty) = n + 1u;
                                                   },
                                                   [](uint32_t) { return false; });
                 if (etid == 0)
                     s_need_select = 0;
                 cta_sync<kTcEpiThreads>();
             }
-            if (*reinterpret_cast<volatile unsigned int*>(&s_any_dirty) == 0) {
+            if (*reinterpret_cast<volatile unsigned int*>(&s_any_dirty) != n + 1u) {
                 maint_done();
                 continue; // no threshold moved: nothing to prune, no filter to refresh
             }
@@ -653,9 +661,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     refresh_filter();
                 }
             }
-            cta_sync<kTcEpiThreads>(); // (everybody has seen the flag before it is cleared; pruned counts are final)
-            if (etid == 0)
-                s_any_dirty = 0;
+            cta_sync<kTcEpiThreads>(); // (pruned counts are final before the next tile appends)
             maint_done();
         }
         if (etid == 0)
