@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
     bool alive = true; // false once a pipeline wait of this thread gave up
 #define TC_WAIT(bar, parity, site)                                                               \
     do {                                                                                         \
-        if (tp.fault == 5 && (site) != 0 && (site) != 3) { /* timing experiment: free-running roles */ \
+        if ((tp.fault == 5 || tp.fault == 8) && (site) != 0 && (site) != 3) { /* timing experiment: free-running roles */ \
         } else {                                                                                 \
             const long long t_w = tp.dbg ? clock64() : 0;                                        \
             alive = tc_wait(bar, parity, &s_abort, &s_error, p.spin_timeout_ns);                 \
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 tc_commit(&s_tmem_full[buf]);
             __syncwarp();
         }
-        if (!alive || tp.fault == 5) { // gave up: let the MMAs in flight finish before tensor memory is released
+        if (!alive || tp.fault == 5 || tp.fault == 8) { // gave up: let the MMAs in flight finish before tensor memory is released
             if (leader) {
                 tc_commit(&s_drain);
                 const unsigned long long t0 = global_ns();
@@ -473,13 +473,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 uint8_t* dst = slabs + sslot * kTcSlabBytes + tc_slab_offset(e * 16u, lane);
                 const uint32_t m0 = 0x01010101u << (2u * g), m1 = m0 << 1;
                 const long long t_a = tp.dbg ? clock64() : 0;
-                if (tp.fault != 2 && tp.fault != 4) { // (faults 2-4: timing experiments with void results)
+                if (tp.fault != 2 && tp.fault != 8) { // (faults 2, 3, 5, 8: timing experiments with void results)
 #pragma unroll
                     for (int i = 0; i < 16; i++) // row 16e+i: + (i >> 3) row groups, + (i & 7) rows
                         *reinterpret_cast<uint2*>(dst + (i >> 3) * kTcSbo + (i & 7) * 16) = make_uint2(w[i] & m0, w[i] & m1);
                 }
                 const long long t_b = tp.dbg ? clock64() : 0;
-                if (tp.fault != 2 && tp.fault != 4)
+                if (tp.fault != 2 && tp.fault != 8)
                     fence_proxy_async_smem(); // the tensor core reads the slab through the async proxy
                 __syncwarp();
                 if (tp.dbg) {
@@ -525,6 +525,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
         refresh_filter();
         for (uint32_t n = 0; n < n_local && alive; n++) {
             const uint32_t t = blockIdx.x + n * gridDim.x, buf = n & 1u;
+            if (tp.fault == 8)
+                continue; // (timing experiment: tensor pipe and TMA alone)
             ex.row0 = t * kTcTileRows;
             // Every value of a CTA's first tile is a candidate (threshold 0).  The first thresholds need
             // k of them per query, not 128 per CTA: only the first 16 CTAs count theirs, the other
@@ -580,7 +582,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                     m = fmaxf(m, __fmaf_rn(slope, f.z, __uint_as_float(kTcMagicBits | v[c & 1][4 * i + 2])));
                     m = fmaxf(m, __fmaf_rn(slope, f.w, __uint_as_float(kTcMagicBits | v[c & 1][4 * i + 3])));
                 }
-                if (m >= thr && !aborted && tp.fault != 6) { // rare: a call, so that the hot loop stays small
+                if (m >= thr && !aborted) { // rare: a call, so that the hot loop stays small
                     if (tp.dbg)
                         dbg_acc[3]++; // (GSB_TC_DEBUG: chunks of lane 0's query that pass level 1)
                     tc_level2(ex, slope, thr, pdf + c * 16, half * 64u + c * 16u, v[c & 1][0], v[c & 1][1], v[c & 1][2],

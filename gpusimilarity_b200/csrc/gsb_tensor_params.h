@@ -30,7 +30,8 @@ struct TensorParams {
     unsigned int* ghist;      // [nq][kSlicedHistBuckets] scores of all candidates so far; zero on entry
     unsigned long long* gtau; // [nq] thresholds shared by all CTAs; zero on entry
     uint32_t n_tiles;         // 128-row tiles of the shard
-    uint32_t fault;           // test hook (GSB_TC_FAULT=1): CTA 0 never loads its first tile -> pipeline timeout
+    uint32_t fault;           // test hook (GSB_TC_FAULT=1): CTA 0 never loads its first tile -> pipeline timeout;
+                              // 2, 3, 5, 8: timing experiments with void results (profiles/r02_tensor.md)
     uint32_t variant;         // GSB_TC_VARIANT=1: every CTA's first tile feeds the histograms (timing experiment)
     unsigned long long* dbg;  // GSB_TC_DEBUG=1: [grid][20 warps][8] clocks spent in each pipeline wait, role time
 };
