@@ -136,6 +136,9 @@ struct SelectSet {
     unsigned long long* cta_keys = nullptr;
     uint32_t* cta_counts = nullptr;
     uint64_t cta_keys_cap = 0; // entries
+    unsigned long long* tail_lists = nullptr; // [grid][cap]: select without a grid barrier (GSB_TAIL)
+    uint32_t* tail_counts = nullptr;          // [4096]
+    uint64_t tail_cap = 0;                    // entries
 };
 
 // Result record of one host-buffer query in MAPPED pinned host memory: the last CTA of the launch
@@ -517,13 +520,37 @@ int ws_recover(Shard& sh)
     return GSB_OK;
 }
 
+// GSB_TAIL=1 (opt-in): the single-query kernel's grid-wide select without a grid barrier — every CTA
+// leaves its candidates in global memory and goes, the one with the last ticket selects
+// (gsb_kernels.cuh, tail_select).  Needs no co-resident grid, but measures slower than the default
+// form (all CTAs line up on an arrival counter, each adds its share of the final list): the barrier
+// costs a CTA 7 us, the lone last CTA needs 15 - 80 us for what 148 CTAs do in 10
+// (profiles/r02_fixed_cost.md).
+bool tail_mode()
+{
+    return env_int("GSB_TAIL", 0) != 0;
+}
+
 // slot < 0: results go to caller-provided (device) buffers, no record needed.
-int ws_reserve(Shard& sh, uint32_t k, int grid, int slot)
+int ws_reserve(Shard& sh, uint32_t k, int grid, int slot, uint32_t cap)
 {
     Workspace& ws = sh.ws;
     GSB_CUDA(cudaSetDevice(sh.device));
     const uint64_t need = static_cast<uint64_t>(grid) * std::max<uint32_t>(k, 1);
+    const uint64_t need_tail = tail_mode() ? static_cast<uint64_t>(grid) * cap : 0;
     for (SelectSet& set : ws.sets) {
+        if (need_tail > set.tail_cap) {
+            if (set.tail_lists) {
+                GSB_CUDA(cudaStreamSynchronize(ws.stream)); // a launch may still be using the old one
+                GSB_CUDA(cudaFree(set.tail_lists));
+            }
+            set.tail_lists = nullptr;
+            set.tail_cap = 0;
+            GSB_CUDA(cudaMalloc(&set.tail_lists, need_tail * 8));
+            set.tail_cap = need_tail;
+            if (!set.tail_counts)
+                GSB_CUDA(cudaMalloc(&set.tail_counts, sizeof(uint32_t) * 4096));
+        }
         if (need > set.cta_keys_cap) {
             if (set.cta_keys) {
                 GSB_CUDA(cudaStreamSynchronize(ws.stream)); // a launch may still be using the old one
@@ -577,6 +604,8 @@ void ws_free(Shard& sh)
         cudaFree(set.gfinal);
         cudaFree(set.cta_keys);
         cudaFree(set.cta_counts);
+        cudaFree(set.tail_lists);
+        cudaFree(set.tail_counts);
     }
     for (ResultSlot& rs : ws.slots)
         if (rs.host)
@@ -744,6 +773,10 @@ void fill_params(const gsb_db* db, Shard& sh, const Plan& plan, uint32_t k, floa
     p->ghist = set.ghist;
     p->ehist = env_int("GSB_SHARE_HIST", 0) ? set.ehist : nullptr; // opt-in: fewer selects, same throughput (profiles/r02_fixed_cost.md)
     p->gfinal = set.gfinal;
+    if (tail_mode() && set.tail_lists && static_cast<uint64_t>(plan.grid) * plan.cap <= set.tail_cap) {
+        p->tail_lists = set.tail_lists;
+        p->tail_counts = set.tail_counts;
+    }
     p->spin_timeout_ns = spin_timeout_ns();
     p->metric = db->metric;
     p->alpha = db->alpha;
@@ -810,7 +843,7 @@ int enqueue_scan(const gsb_db* db, const uint32_t* q_dev_words, uint32_t k, floa
         int rc = make_plan(db->layout, sh, k, &plan);
         if (rc)
             return rc;
-        rc = ws_reserve(sh, k, plan.grid, slot);
+        rc = ws_reserve(sh, k, plan.grid, slot, plan.cap);
         if (rc)
             return rc;
         GSB_CUDA(cudaSetDevice(sh.device));
@@ -2330,7 +2363,7 @@ int gsb_db_search_enqueue(const gsb_db* db, void* stream, const int32_t* h_query
     int rc = make_plan(db->layout, sh, k, &plan);
     if (rc)
         return rc;
-    rc = ws_reserve(sh, k, plan.grid, -1);
+    rc = ws_reserve(sh, k, plan.grid, -1, plan.cap);
     if (rc)
         return rc;
     GSB_CUDA(cudaSetDevice(sh.device));

@@ -316,7 +316,8 @@ def test_tuning_knobs_do_not_change_results(monkeypatch):
     for env in ({"GSB_STAGES": "2"}, {"GSB_STAGES": "4", "GSB_WARPS": "8"}, {"GSB_GRID": "7"},
                 {"GSB_GRID": "1", "GSB_WARPS": "12"}, {"GSB_ROWPOP": "0", "GSB_WARPS": "4"},
                 {"GSB_ROWPOP": "0"}, {"GSB_MIN_CAP": "8192", "GSB_WARPS": "8"}, {"GSB_SHARE_HIST": "1"},
-                {"GSB_SHARE_HIST": "1", "GSB_GRID": "9"}, {"GSB_PDL": "0"}, {"GSB_PDL": "0", "GSB_SHARE_HIST": "1"}):
+                {"GSB_SHARE_HIST": "1", "GSB_GRID": "9"}, {"GSB_PDL": "0"}, {"GSB_PDL": "0", "GSB_SHARE_HIST": "1"},
+                {"GSB_TAIL": "1"}, {"GSB_TAIL": "1", "GSB_PDL": "0"}, {"GSB_TAIL": "1", "GSB_GRID": "5"}):
         for k_, v in env.items():
             monkeypatch.setenv(k_, v)
         db = make_db(rows_np)
@@ -326,6 +327,31 @@ def test_tuning_knobs_do_not_change_results(monkeypatch):
             monkeypatch.delenv(k_)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tail", ["1", "0"])
+def test_select_with_and_without_grid_barrier(monkeypatch, tail):
+    """GSB_TAIL=0 (default): grid-wide arrival counter, every CTA adds its share of the final list;
+    GSB_TAIL=1: the CTAs leave their candidates in global memory and go, the CTA with the last ticket
+    selects out of all the lists (tail_select).  3 M rows (every SM busy), a tie group around k (crowded boundary
+    bucket: the streaming path), cutoffs, k from 1 to the peeling passes, repeated and back-to-back
+    asynchronous queries (both control sets, lists and histograms must be left clean)."""
+    monkeypatch.setenv("GSB_TAIL", tail)
+    n = 3_000_000
+    rows_np = OC.c_synth_db(1234, n, 32, 1500)
+    rows_np[700_000:706_000] = rows_np[11]                         # 6000 equal rows: more ties than the buffer holds
+    db = make_db(rows_np)
+    for rep in range(2):
+        for q in (O.synth_template(1234, 32), rows_np[11], rows_np[n - 1]):
+            for k, cutoff in ((1000, 0.0), (1, 0.0), (1000, 0.12), (4000, 0.0), (20000, 0.0)):
+                check(db, rows_np, q, k, cutoff, f"tail {tail} rep {rep}")
+    qs = [rows_np[i] for i in (3, 11, 2_999_999, 1_500_000)]
+    tickets = [db.search_rows_async(q, 500, 0.0) for q in qs]
+    for q, t in zip(qs, tickets):
+        assert_same(db.search_rows_wait(t), OC.c_search(q, rows_np, 500, 0.0), f"tail {tail} async")
+    db.close()
+
+
+@pytest.mark.gpu
 def test_grid_wide_threshold_sharing(monkeypatch):
     """GSB_SHARE_HIST=1: every candidate that goes through a select is counted in a grid-wide histogram
     whose k-th bucket bounds the threshold of every CTA.  3 M rows (every SM busy), ties, cutoffs, k up
