@@ -610,7 +610,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) scan_tensor_kernel(const __grid
                 if (tp.dbg)
                     dbg_acc[4] += clock64() - t_m; // (GSB_TC_DEBUG: epilogue slot 4 = maintenance)
             };
-            // thread (half 0, lane) owns query qj: adopt the grid-wide threshold if it rose
+            // thread (half 0, lane) owns query qj: adopt the grid-wide threshold if it rose.  (The
+            // partner thread of the other half tile may still be in tc_exact and read s_tau[qj] while
+            // it is written here: one aligned 64-bit store, and either value is a valid lower bound.)
             const bool adopted = live && half == 0 && g_seen > s_tau[qj];
             if (adopted)
                 s_tau[qj] = g_seen;
