@@ -80,6 +80,31 @@ def test_tensor_kernel_dense_queries_full_grid(monkeypatch):
             assert_same(got[j], OC.c_search(qs[j], rows_np, 100, cutoff), f"oracle, query {j}, cutoff {cutoff}")
 
 
+def test_tensor_kernel_full_size(monkeypatch):
+    """200 M synthetic rows in HBM (10 500 tiles per CTA: thresholds converge, lists are pruned, the
+    pipeline runs for tens of milliseconds): dense and sparse queries through the tensor-core kernel
+    against the streamed oracle (every row scored on the host cores), the single-query kernel and the
+    bit-sliced kernel, with and without a cutoff."""
+    n, seed, plant, k = 200_000_000, 77, 50000, 100
+    whole = gsb.FingerprintDB.synthetic(n, device=0, seed=seed, plant_period=plant)
+    rng = np.random.default_rng(n)
+    qs = np.concatenate([O.synth_template(seed, 32)[None, :],
+                         np.stack([whole.getFingerprint(int(r)) for r in rng.integers(0, n, 11)]),
+                         _dense_queries(rng, 6, 200), _dense_queries(rng, 6, 512)])
+    for cutoff in (0.0, 0.1):
+        monkeypatch.setenv("GSB_BATCH_KERNEL", "4")
+        got = whole.search_batch_rows(qs, k, cutoff)
+        monkeypatch.setenv("GSB_BATCH_KERNEL", "3")
+        want = whole.search_batch_rows(qs, k, cutoff)
+        for j in range(len(qs)):
+            assert_same(got[j], want[j], f"full size, tensor vs bit-sliced, query {j}, cutoff {cutoff}")
+        for j in (0, 5, 14, 20):
+            assert_same(got[j], whole.search_rows(qs[j], k, cutoff), f"full size, tensor vs single-query kernel, query {j}")
+        for j in ((0, 13) if cutoff == 0.0 else (1,)):
+            assert_same(got[j], OC.c_stream_search(qs[j], seed, plant, n, k, cutoff), f"full size, streamed oracle, query {j}")
+    whole.close()
+
+
 def test_tensor_kernel_choice(monkeypatch):
     """Automatic dispatch: the set bits of the batch decide between the bit-sliced kernel (cost per set
     bit) and the tensor-core kernel (cost per 128 queries); other row widths and metrics never get it."""
