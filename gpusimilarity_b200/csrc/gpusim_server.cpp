@@ -579,7 +579,7 @@ int gsb_server_listen(gsb_server* srv, const char* socket_path)
         const int fd = socket(AF_UNIX, SOCK_STREAM, 0);
         if (fd < 0)
             break;
-        if (bind(fd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0 && listen(fd, 16) == 0) {
+        if (bind(fd, reinterpret_cast<sockaddr*>(&addr), sizeof(addr)) == 0 && listen(fd, 128) == 0) { // (QLocalServer's own backlog is 50)
             srv->listen_fd = fd;
             return GSB_OK;
         }

@@ -6,6 +6,7 @@ from __future__ import annotations
 import ctypes as C
 import socket
 import struct
+import time
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -131,7 +132,15 @@ def search_over_socket(request: bytes, socket_path: str = SOCKET_PATH, timeout: 
     """Client side: one request, one response (gpusim_search.py:49-52)."""
     with socket.socket(socket.AF_UNIX, socket.SOCK_STREAM) as s:
         s.settimeout(timeout)
-        s.connect(socket_path)
+        deadline = time.monotonic() + timeout
+        while True:
+            try:
+                s.connect(socket_path)
+                break
+            except BlockingIOError:   # the daemon's accept queue is full: a unix socket says EAGAIN at once
+                if time.monotonic() > deadline:
+                    raise
+                time.sleep(0.0005)
         s.sendall(request)
         buf = b""
         while True:
