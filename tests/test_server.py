@@ -83,6 +83,32 @@ def test_socket_server_thread(two_dbs, small_db, tmp_path):
     assert not th.is_alive()
 
 
+def test_many_clients_at_once(two_dbs, small_db, tmp_path):
+    """80 clients connect at the same moment (more than the accept queue held before: a unix socket
+    refuses the surplus with EAGAIN): every one gets its own, right answer."""
+    n = 80
+    server = GPUSimServer([two_dbs[0]], use_gpu=False)
+    path = str(tmp_path / "crowd.sock")
+    server.listen(path)
+    th = threading.Thread(target=server.serve, args=(n,), daemon=True)
+    th.start()
+    out = [None] * n
+    go = threading.Barrier(n)
+
+    def client(i):
+        go.wait()
+        out[i] = decode_response(search_over_socket(encode_request({"small": "pass"}, 5000 + i, 3, 0.0, small_db[i % 100]), path))
+
+    clients = [threading.Thread(target=client, args=(i,)) for i in range(n)]
+    for c in clients:
+        c.start()
+    for c in clients:
+        c.join(timeout=60)
+    th.join(timeout=10)
+    for i, r in enumerate(out):
+        assert r is not None and r[0] == 5000 + i and len(r[2]) == 3 and r[4][0] == 1.0, i
+
+
 def test_hostile_requests_do_not_hurt_the_daemon(two_dbs, small_db, tmp_path):
     """a result count of 2^31-1 is clamped to the row count (no 16 GB allocation, no
     exception through the C ABI); a request that fails (wrong query width) still gets a well-formed
