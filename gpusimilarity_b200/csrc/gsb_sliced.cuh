@@ -564,14 +564,22 @@ __global__ void __launch_bounds__(CW * 32, 1) scan_sliced_kernel(const __grid_co
             const unsigned long long tau = s_tau[j];
             unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
             uint32_t out = 0;
-            for (uint32_t base = 0; base < n; base += 32) {
-                const unsigned long long key = base + lane < n ? list[base + lane] : 0ull;
+            // (the list lives in global memory: four independent loads per lane in flight, then the in-place
+            // compaction of those 128 entries — writes never pass what has been read)
+            for (uint32_t base = 0; base < n; base += 128) {
+                unsigned long long key[4];
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    key[e] = base + e * 32 + lane < n ? list[base + e * 32 + lane] : 0ull;
                 __syncwarp();
-                const bool keep = key > tau;
-                const unsigned km = __ballot_sync(kFull, keep);
-                if (keep)
-                    list[out + __popc(km & ((1u << lane) - 1u))] = key;
-                out += __popc(km);
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    const bool keep = key[e] > tau;
+                    const unsigned km = __ballot_sync(kFull, keep);
+                    if (keep)
+                        list[out + __popc(km & ((1u << lane) - 1u))] = key[e];
+                    out += __popc(km);
+                }
             }
             __syncwarp();
             if (lane == 0) {
