@@ -100,13 +100,23 @@ __device__ void batch_finish(const BatchParams& p, const CandShared& cs, unsigne
     const bool drop_zero = p.cutoff > 0.0f;
     __threadfence_block();
     batch_select_round<NT>(cs, my_cand, s_cnt, s_tau, nq, p.k, true, tid, [](uint32_t) {}, sorted);
-    for (uint32_t j = 0; j < nq; j++) {
-        const uint32_t n = s_cnt[j];
+    // a warp per list (one list after the other with the whole CTA is a chain of nq dependent
+    // global load -> store round trips: 0.3 ms of a 1024-query pass)
+    for (uint32_t j = tid >> 5; j < nq; j += NT / 32) {
+        const uint32_t n = s_cnt[j], lane = tid & 31;
         const unsigned long long* list = my_cand + (uint64_t) j * kBatchListCap;
         unsigned long long* dst = p.qlists + ((uint64_t) blockIdx.x * nq + j) * p.k;
-        for (uint32_t i = tid; i < n; i += NT)
-            dst[i] = list[i];
-        if (tid == 0) {
+        for (uint32_t i0 = 0; i0 < n; i0 += 128) {
+            unsigned long long key[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                key[e] = i0 + e * 32 + lane < n ? list[i0 + e * 32 + lane] : 0ull;
+#pragma unroll
+            for (int e = 0; e < 4; e++)
+                if (i0 + e * 32 + lane < n)
+                    dst[i0 + e * 32 + lane] = key[e];
+        }
+        if (lane == 0) {
             p.qcounts[blockIdx.x * nq + j] = n;
             if (drop_zero && s_surv[j])
                 atomicAdd(&p.surv_acc[j], s_surv[j]);
