@@ -9,3 +9,5 @@ for tool in memcheck racecheck synccheck; do
 done
 GSB_TAIL=1 timeout -s KILL 400 compute-sanitizer --tool memcheck --kernel-regex kns=scan_topk python -m pytest tests/test_gpu_parity.py -q -m gpu -k "ties or sizes_and_ragged" > gpurun_out/sanitize_tail_memcheck.log 2>&1
 echo "tail memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_tail_memcheck.log | tail -3
+GSB_BATCH_KERNEL=3 timeout -s KILL 400 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -m gpu -k "sliced_kernel_ties_blocks_and_groups or sharded_multi_query_merge" > gpurun_out/sanitize_sliced_memcheck.log 2>&1
+echo "sliced memcheck rc=$?"; grep -E "ERROR SUMMARY|passed|failed" gpurun_out/sanitize_sliced_memcheck.log | tail -3
